@@ -1,0 +1,461 @@
+// capi.cu -- the C ABI (include/cgmres_b200.h): handle bookkeeping, host<->device
+// staging and stream-ordered launches.  No arithmetic of the control law lives here
+// except get_dtau (cgmres.hpp:32-34), which is batch-uniform and evaluated once per
+// step with the host libm so that it is bit-identical to the reference's.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <string>
+
+#include "cgmres_b200.h"
+#include "cgmres_b200/models.hpp"
+#include "kernel_args.h"
+
+namespace cgmres_b200 {
+
+template <class M, class Sim>
+static ModelInfo make_info(const char* name) {
+  ModelInfo i;
+  i.dim_x = M::dim_x;
+  i.dim_u = M::dim_u;
+  i.dim_p = M::dim_p;
+  i.dv = M::dv;
+  i.k_max = M::k_max;
+  i.n_ctrl = M::control_input;
+  i.dt = M::dt;
+  i.h = M::h;
+  i.zeta = M::zeta;
+  i.Tf = M::Tf;
+  i.alpha = M::alpha;
+  i.tol = M::tol;
+  i.plant_dt = Sim::dt;
+  i.name = name;
+  return i;
+}
+
+const ModelInfo* model_info(int model) {
+  static const ModelInfo infos[MODEL_COUNT] = {
+      make_info<MassSpringDamperModel, MassSpringDamperSimulator>("mass_spring_damper"),
+      make_info<ArmPendulumModel, ArmPendulumSimulator>("arm_type_inverted_pendulum"),
+      make_info<SemiactiveDamperModel, SemiactiveDamperSimulator>("semiactive_damper"),
+  };
+  return (model >= 0 && model < MODEL_COUNT) ? &infos[model] : nullptr;
+}
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(CGMRES_B200_ECUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CU(call)                                       \
+  do {                                                 \
+    cudaError_t e_ = (call);                           \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+}  // namespace cgmres_b200
+
+using namespace cgmres_b200;
+
+struct cgmres_b200_controller {
+  int model = 0, mode = 0, device = 0;
+  int64_t n = 0, ld = 0;
+  const ModelInfo* mi = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  double t = 0.0;          // cgmres.hpp:195 -- all instances of a handle step in lock step
+  bool ptau_full = false;  // false: ptau holds one p per instance (set_ptau_repeat)
+  double *x = nullptr, *U = nullptr, *dUdt = nullptr, *ptau = nullptr, *F1 = nullptr, *V = nullptr, *xtau = nullptr,
+         *u_out = nullptr;
+  int32_t* status = nullptr;
+  double* stage = nullptr;  // instance-major staging, grown on demand
+  size_t stage_doubles = 0;
+
+  int L() const { return mi->L(); }
+  int ptau_rows_full() const { return (mi->dv + 1) * mi->dim_p; }
+
+  int ensure_stage(size_t doubles) {
+    if (doubles <= stage_doubles) return 0;
+    if (stage) {
+      CU(cudaStreamSynchronize(stream));
+      CU(cudaFree(stage));
+      stage = nullptr;
+      stage_doubles = 0;
+    }
+    CU(cudaMalloc(&stage, sizeof(double) * doubles));
+    stage_doubles = doubles;
+    return 0;
+  }
+
+  template <class T>
+  int dalloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc(p, sizeof(T) * (count ? count : 1));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    e = cudaMemsetAsync(*p, 0, sizeof(T) * (count ? count : 1), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    return 0;
+  }
+
+  int allocate() {
+    const size_t l = (size_t)ld, Lz = (size_t)L();
+    int rc;
+    if ((rc = dalloc(&x, l * mi->dim_x))) return rc;
+    if ((rc = dalloc(&U, l * Lz))) return rc;
+    if ((rc = dalloc(&dUdt, l * Lz))) return rc;  // zero: the de-facto contract of cgmres.hpp:14
+    if ((rc = dalloc(&ptau, l * (size_t)ptau_rows_full()))) return rc;
+    if ((rc = dalloc(&F1, l * Lz))) return rc;
+    if ((rc = dalloc(&V, l * Lz * (size_t)(mi->k_max + 1)))) return rc;
+    if ((rc = dalloc(&xtau, l * (size_t)mi->dim_x * (size_t)(mi->dv > 1 ? mi->dv - 1 : 1)))) return rc;
+    if ((rc = dalloc(&u_out, l * mi->dim_u))) return rc;
+    if ((rc = dalloc(&status, l))) return rc;
+    if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;
+    return 0;
+  }
+
+  void release() {
+    cudaFree(x);
+    cudaFree(U);
+    cudaFree(dUdt);
+    cudaFree(ptau);
+    cudaFree(F1);
+    cudaFree(V);
+    cudaFree(xtau);
+    cudaFree(u_out);
+    cudaFree(status);
+    cudaFree(stage);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+
+  double dtau(double tt) const { return mi->Tf * (1 - exp(-mi->alpha * tt)) / (double)mi->dv; }
+
+  // one update for every instance; plant=1 also advances x (closed loop on device)
+  int launch_update(int plant) {
+    if (mode != CGMRES_B200_MODE_EXACT) return fail(CGMRES_B200_ENOTIMPL, "fast mode not built for this model");
+    ExactArgs a;
+    a.n = n;
+    a.ld = ld;
+    a.x = x;
+    a.U = U;
+    a.dUdt = dUdt;
+    a.ptau = ptau;
+    a.F1 = F1;
+    a.V = V;
+    a.xtau = xtau;
+    a.u_out = u_out;
+    a.status = status;
+    a.dtau_t = dtau(t);
+    a.dtau_th = dtau(t + mi->h);
+    a.plant = plant;
+    CU(exact_launch_control(model, ptau_full, a, stream));
+    g_launches++;
+    t = t + mi->dt;  // cgmres.hpp:107 (accumulated, not i*dt)
+    return 0;
+  }
+
+  // host instance-major -> device SoA rows
+  int upload_rows(const double* host, double* soa, int rows) {
+    if (rows == 0 || n == 0) return 0;
+    int rc = ensure_stage((size_t)n * rows);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(stage, host, sizeof(double) * (size_t)n * rows, cudaMemcpyHostToDevice, stream));
+    CU(launch_aos_to_soa(stage, soa, n, rows, ld, stream));
+    g_launches++;
+    return 0;
+  }
+  int download_rows(double* host, const double* soa, int rows) {
+    if (rows == 0 || n == 0) return 0;
+    int rc = ensure_stage((size_t)n * rows);
+    if (rc) return rc;
+    CU(launch_soa_to_aos(soa, stage, n, rows, ld, stream));
+    g_launches++;
+    CU(cudaMemcpyAsync(host, stage, sizeof(double) * (size_t)n * rows, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+};
+
+#define CHECK_H(h) \
+  if (!(h)) return fail(CGMRES_B200_EINVAL, "null handle")
+#define ON_DEVICE(h) CU(cudaSetDevice((h)->device))
+
+extern "C" {
+
+const char* cgmres_b200_last_error(void) { return g_err.c_str(); }
+
+int cgmres_b200_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return c;
+}
+
+int cgmres_b200_model_dims(int model, int* dims) {
+  const ModelInfo* mi = model_info(model);
+  if (!mi || !dims) return fail(CGMRES_B200_EINVAL, "unknown model");
+  dims[0] = mi->dim_x;
+  dims[1] = mi->dim_u;
+  dims[2] = mi->dim_p;
+  dims[3] = mi->dv;
+  dims[4] = mi->k_max;
+  dims[5] = mi->n_ctrl;
+  return 0;
+}
+
+int cgmres_b200_model_params(int model, double* par) {
+  const ModelInfo* mi = model_info(model);
+  if (!mi || !par) return fail(CGMRES_B200_EINVAL, "unknown model");
+  par[0] = mi->dt;
+  par[1] = mi->h;
+  par[2] = mi->zeta;
+  par[3] = mi->Tf;
+  par[4] = mi->alpha;
+  par[5] = mi->tol;
+  return 0;
+}
+
+const char* cgmres_b200_model_name(int model) {
+  const ModelInfo* mi = model_info(model);
+  return mi ? mi->name : nullptr;
+}
+
+int cgmres_b200_create(int model, int64_t n, int device, int mode, cgmres_b200_handle* out) {
+  if (!out) return fail(CGMRES_B200_EINVAL, "out is null");
+  *out = nullptr;
+  const ModelInfo* mi = model_info(model);
+  if (!mi) return fail(CGMRES_B200_EINVAL, "unknown model id");
+  if (n < 0) return fail(CGMRES_B200_EINVAL, "negative instance count");
+  if (mode != CGMRES_B200_MODE_EXACT && mode != CGMRES_B200_MODE_FAST) return fail(CGMRES_B200_EINVAL, "unknown mode");
+  if (mode == CGMRES_B200_MODE_FAST) return fail(CGMRES_B200_ENOTIMPL, "fast mode not built for this model");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(CGMRES_B200_ECUDA, "no usable CUDA device (this library has no CPU path)");
+  }
+  if (device < 0 || device >= count) return fail(CGMRES_B200_EINVAL, "device index out of range");
+  CU(cudaSetDevice(device));
+  cgmres_b200_controller* h = new (std::nothrow) cgmres_b200_controller();
+  if (!h) return fail(CGMRES_B200_ENOMEM, "host allocation failed");
+  h->model = model;
+  h->mode = mode;
+  h->device = device;
+  h->n = n;
+  h->ld = (n + 31) & ~(int64_t)31;
+  if (h->ld == 0) h->ld = 32;
+  h->mi = mi;
+  e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail(e, "cudaStreamCreate");
+  }
+  h->stream = h->own_stream;
+  int rc = h->allocate();
+  if (rc == 0) {
+    e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  if (rc) {
+    h->release();
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int cgmres_b200_destroy(cgmres_b200_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->release();
+  delete h;
+  return 0;
+}
+
+int64_t cgmres_b200_size(cgmres_b200_handle h) { return h ? h->n : -1; }
+int cgmres_b200_model(cgmres_b200_handle h) { return h ? h->model : -1; }
+int cgmres_b200_mode(cgmres_b200_handle h) { return h ? h->mode : -1; }
+
+int cgmres_b200_set_stream(cgmres_b200_handle h, void* stream) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+  return 0;
+}
+void* cgmres_b200_get_stream(cgmres_b200_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int cgmres_b200_synchronize(cgmres_b200_handle h) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+double cgmres_b200_get_dtau(cgmres_b200_handle h, double t) { return h ? h->dtau(t) : 0.0; }
+
+int cgmres_b200_set_ptau(cgmres_b200_handle h, const double* ptau) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (h->mi->dim_p == 0) return 0;
+  if (!ptau) return fail(CGMRES_B200_EINVAL, "ptau is null");
+  int rc = h->upload_rows(ptau, h->ptau, h->ptau_rows_full());
+  if (rc) return rc;
+  h->ptau_full = true;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cgmres_b200_set_ptau_repeat(cgmres_b200_handle h, const double* p) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (h->mi->dim_p == 0) return 0;
+  if (!p) return fail(CGMRES_B200_EINVAL, "p is null");
+  int rc = h->upload_rows(p, h->ptau, h->mi->dim_p);
+  if (rc) return rc;
+  h->ptau_full = false;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cgmres_b200_init_u0(cgmres_b200_handle h, const double* u0) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!u0) return fail(CGMRES_B200_EINVAL, "u0 is null");
+  const int nu = h->mi->dim_u;
+  int rc = h->ensure_stage((size_t)h->n * nu);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->stage, u0, sizeof(double) * (size_t)h->n * nu, cudaMemcpyHostToDevice, h->stream));
+  CU(launch_broadcast_rows(h->stage, h->U, h->n, nu, h->mi->dv, h->ld, h->stream));
+  g_launches++;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cgmres_b200_init_u0_newton(cgmres_b200_handle h, double* u0, const double* x0, const double* p0, int n_loop) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  const int nu = h->mi->dim_u, nx = h->mi->dim_x, np = h->mi->dim_p;
+  if (!u0 || !x0 || (np > 0 && !p0) || n_loop < 0) return fail(CGMRES_B200_EINVAL, "bad init_u0_newton arguments");
+  const size_t n = (size_t)h->n;
+  int rc = h->ensure_stage(n * (size_t)(nu + nx + np + 1));
+  if (rc) return rc;
+  double* d_u = h->stage;
+  double* d_x = d_u + n * nu;
+  double* d_p = d_x + n * nx;
+  CU(cudaMemcpyAsync(d_u, u0, sizeof(double) * n * nu, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_x, x0, sizeof(double) * n * nx, cudaMemcpyHostToDevice, h->stream));
+  if (np > 0) CU(cudaMemcpyAsync(d_p, p0, sizeof(double) * n * np, cudaMemcpyHostToDevice, h->stream));
+  CU(exact_launch_newton(h->model, h->n, h->ld, d_u, d_x, d_p, np, n_loop, h->U, h->stream));
+  g_launches++;
+  CU(cudaMemcpyAsync(u0, d_u, sizeof(double) * n * nu, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cgmres_b200_control_dev(cgmres_b200_handle h, double* u_dev, const double* x_dev) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!u_dev || !x_dev) return fail(CGMRES_B200_EINVAL, "null device pointer");
+  CU(launch_aos_to_soa(x_dev, h->x, h->n, h->mi->dim_x, h->ld, h->stream));
+  g_launches++;
+  int rc = h->launch_update(0);
+  if (rc) return rc;
+  CU(launch_soa_to_aos(h->u_out, u_dev, h->n, h->mi->dim_u, h->ld, h->stream));
+  g_launches++;
+  return 0;
+}
+
+int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!u || !x) return fail(CGMRES_B200_EINVAL, "null pointer");
+  const size_t n = (size_t)h->n;
+  const int nx = h->mi->dim_x, nu = h->mi->dim_u;
+  int rc = h->ensure_stage(n * (size_t)(nx + nu));
+  if (rc) return rc;
+  double* d_x = h->stage;
+  double* d_u = h->stage + n * nx;
+  CU(cudaMemcpyAsync(d_x, x, sizeof(double) * n * nx, cudaMemcpyHostToDevice, h->stream));
+  rc = cgmres_b200_control_dev(h, d_u, d_x);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(u, d_u, sizeof(double) * n * nu, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cgmres_b200_set_x(cgmres_b200_handle h, const double* x) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!x) return fail(CGMRES_B200_EINVAL, "x is null");
+  int rc = h->upload_rows(x, h->x, h->mi->dim_x);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int cgmres_b200_get_x(cgmres_b200_handle h, double* x) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!x) return fail(CGMRES_B200_EINVAL, "x is null");
+  return h->download_rows(x, h->x, h->mi->dim_x);
+}
+int cgmres_b200_get_u(cgmres_b200_handle h, double* u) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!u) return fail(CGMRES_B200_EINVAL, "u is null");
+  return h->download_rows(u, h->u_out, h->mi->dim_u);
+}
+
+int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (n_steps < 0) return fail(CGMRES_B200_EINVAL, "negative step count");
+  for (int s = 0; s < n_steps; s++) {
+    int rc = h->launch_update(1);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int cgmres_b200_get_state(cgmres_b200_handle h, double* t, double* U, double* dUdt) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (t) *t = h->t;
+  int rc = 0;
+  if (U && (rc = h->download_rows(U, h->U, h->L()))) return rc;
+  if (dUdt && (rc = h->download_rows(dUdt, h->dUdt, h->L()))) return rc;
+  return 0;
+}
+
+int cgmres_b200_set_state(cgmres_b200_handle h, const double* t, const double* U, const double* dUdt) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (t) h->t = *t;
+  int rc = 0;
+  if (U && (rc = h->upload_rows(U, h->U, h->L()))) return rc;
+  if (dUdt && (rc = h->upload_rows(dUdt, h->dUdt, h->L()))) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cgmres_b200_get_status(cgmres_b200_handle h, int32_t* status) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!status) return fail(CGMRES_B200_EINVAL, "status is null");
+  CU(cudaMemcpyAsync(status, h->status, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t cgmres_b200_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

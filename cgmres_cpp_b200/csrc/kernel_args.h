@@ -1,0 +1,56 @@
+// kernel_args.h -- internal interface between the C-ABI host code (capi.cu) and the
+// kernel translation units (exact_kernels.cu is built with -fmad=false, fast_kernels.cu
+// with FMA contraction on; they must not share inlined device code at link time, so
+// everything crosses this plain-struct boundary).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cgmres_b200 {
+
+enum { MODEL_MSD = 0, MODEL_ARM = 1, MODEL_SEMIACTIVE = 2, MODEL_COUNT = 3 };
+
+// exit path of the GMRES solve inside one update (status word = code | columns_used << 8)
+enum { EXIT_FULL = 0, EXIT_CONVERGED = 1, EXIT_RHO0 = 2, EXIT_BREAKDOWN = 3 };
+
+struct ModelInfo {
+  int dim_x, dim_u, dim_p, dv, k_max, n_ctrl;
+  double dt, h, zeta, Tf, alpha, tol;
+  double plant_dt;
+  const char* name;
+  int L() const { return dim_u * dv; }
+};
+const ModelInfo* model_info(int model);
+
+// Structure-of-arrays device state of the exact mode: every matrix is [rows][ld],
+// instance index fastest (ld = instance count rounded up to 32).
+struct ExactArgs {
+  int64_t n, ld;
+  double* x;           // [dim_x][ld]      plant state
+  double* U;           // [L][ld]          input trajectory     (cgmres.hpp:196)
+  double* dUdt;        // [L][ld]          its time derivative  (cgmres.hpp:197)
+  const double* ptau;  // [dim_p][ld] (repeat) or [(dv+1)*dim_p][ld] (full)   (cgmres.hpp:200)
+  double* F1;          // [L][ld]          F(U, x+dx*h, t+h)    (cgmres.hpp:202)
+  double* V;           // [(k_max+1)*L][ld] un-normalised Krylov basis (gmres.hpp:11)
+  double* xtau;        // [dim_x*(dv-1)][ld] rollout scratch    (cgmres.hpp:116)
+  double* u_out;       // [dim_u][ld]      u = U[0:dim_u]       (cgmres.hpp:109)
+  int32_t* status;     // [ld]
+  double dtau_t, dtau_th;  // get_dtau(t), get_dtau(t+h) evaluated on the host (cgmres.hpp:32-34)
+  int plant;               // 1: also advance x by one Euler plant step
+};
+
+// exact mode (exact_kernels.cu)
+cudaError_t exact_launch_control(int model, bool ptau_full, const ExactArgs& a, cudaStream_t s);
+cudaError_t exact_launch_newton(int model, int64_t n, int64_t ld, double* u0_aos, const double* x0_aos,
+                                const double* p0_aos, int p_stride, int n_loop, double* U_soa, cudaStream_t s);
+size_t exact_control_smem_bytes(int model, int block);
+
+// layout kernels (layout.cu): instance-major host layout <-> structure of arrays
+//   aos[n][rows]  <->  soa[rows][ld]
+cudaError_t launch_aos_to_soa(const double* aos, double* soa, int64_t n, int rows, int64_t ld, cudaStream_t s);
+cudaError_t launch_soa_to_aos(const double* soa, double* aos, int64_t n, int rows, int64_t ld, cudaStream_t s);
+// soa[(i*rows_per + j)][n] = aos[n][j] for i in 0..reps-1 (init_u0 / set_ptau_repeat broadcasts)
+cudaError_t launch_broadcast_rows(const double* aos, double* soa, int64_t n, int rows_per, int reps, int64_t ld,
+                                  cudaStream_t s);
+
+}  // namespace cgmres_b200

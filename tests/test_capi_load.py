@@ -1,0 +1,64 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what include/cgmres_b200.h
+declares, reports the reference's problem sizes, and fails loudly (never falls back) without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cgmres_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgmres_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_table_agree(built):
+    from cgmres_cpp_b200._lib import SIGNATURES
+
+    assert declared_symbols() == sorted(SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol(built):
+    from cgmres_cpp_b200._lib import LIB_PATH
+
+    l = ctypes.CDLL(LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(l, name), name
+
+
+def test_model_tables_match_reference(built, oracle_port):
+    import cgmres_cpp_b200 as cg
+
+    for m in (cg.MSD, cg.ARM, cg.SEMIACTIVE):
+        d, o = cg.model_dims(m), oracle_port.dims(m)
+        assert (d.dim_x, d.dim_u, d.dim_p, d.dv, d.k_max, d.control_input) == (o.dim_x, o.dim_u, o.dim_p, o.dv,
+                                                                               o.k_max, o.n_ctrl)
+        assert cg.model_params(m) == oracle_port.params(m)
+    assert cg.model_name(cg.MSD) == "mass_spring_damper"
+    with pytest.raises(cg.CgmresB200Error):
+        cg.model_dims(17)
+
+
+def test_no_cpu_fallback(built):
+    import cgmres_cpp_b200 as cg
+
+    if cg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cg.CgmresB200Error, match="no usable CUDA device"):
+        cg.BatchedCgmres(cg.MSD, 8)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cgmres_cpp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text, (dirpath, f)
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.isfile(p):
+            assert "oracle" not in open(p).read().lower(), f

@@ -1,0 +1,271 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/cgmres_b200.h), against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures.
+
+Bars (BASELINE.json north_star): U within 1e-9 relative (inf-norm) per update, closed-loop x within 1e-6 over
+1000 steps.  The exact mode is held to the stronger bar it is built for: bit-identical U, dUdt and x for the
+models without libm calls (mass_spring_damper, semiactive_damper)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = (po.MSD, po.ARM, po.SEMIACTIVE)
+BIT_EXACT = {po.MSD: True, po.SEMIACTIVE: True, po.ARM: False}  # arm calls sin/cos: CUDA libm != glibc
+TOL_U_REL = 1e-9  # per update, teacher forced
+TOL_X_ABS = 1e-6  # closed loop, 1000 steps
+
+
+@pytest.fixture(scope="module")
+def cg(built):
+    import cgmres_cpp_b200 as m
+
+    if m.device_count() == 0:
+        pytest.fail("GPU test selected but no CUDA device is visible (no CPU fallback exists)")
+    return m
+
+
+def gold(model):
+    return np.load(os.path.join(GOLD, f"{po.MODEL_NAMES[model]}.npz"))
+
+
+def rel_inf(a, b):
+    d = np.abs(a - b).max(axis=-1)
+    s = np.abs(b).max(axis=-1)
+    return float((d / np.where(s > 0, s, 1.0)).max())
+
+
+def make(cg, model, x0, p, u0, mode=None, ptau_full=False):
+    c = cg.BatchedCgmres(model, len(x0), device=0, mode=cg.MODE_EXACT if mode is None else mode)
+    if c.dim_p:
+        (c.set_ptau if ptau_full else c.set_ptau_repeat)(p)
+    c.init_u0(u0)
+    p0 = p.reshape(len(x0), -1)[:, :c.dim_p] if c.dim_p else None
+    un = c.init_u0_newton(u0, x0, p0, 10)
+    c.set_x(x0)
+    return c, un
+
+
+def check_pair(model, got, want, what, tol):
+    if BIT_EXACT[model]:
+        assert np.array_equal(got, want), f"{what}: max abs diff {np.abs(got - want).max():.3e} (expected bit-identical)"
+    else:
+        assert np.abs(got - want).max() <= tol, f"{what}: {np.abs(got - want).max():.3e} > {tol}"
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_newton_init_matches_golden(cg, model):
+    g, s = gold(model), po.SHIPPED[model]
+    c, un = make(cg, model, np.array([s["x0"]]), np.array([s["p"]]), np.array(s["u0"]))
+    check_pair(model, un[0], g["newton_u0"], "newton u0", 1e-12)
+    _, U, dUdt = c.get_state()
+    check_pair(model, U[0], np.tile(g["newton_u0"], c.dv), "U after init", 1e-12)
+    assert not dUdt.any()
+    c.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_teacher_forced_update_matches_golden(cg, model):
+    """Load the reference's state before step s, run ONE update on the GPU, compare U/dUdt/u after it."""
+    g, s = gold(model), po.SHIPPED[model]
+    c = cg.BatchedCgmres(model, 1)
+    if c.dim_p:
+        c.set_ptau_repeat([s["p"]])
+    worst = 0.0
+    for i in range(len(g["tf_steps"])):
+        c.set_state(float(g["tf_t"][i]), g["tf_U"][i][None], g["tf_dUdt"][i][None])
+        u = c.control(g["tf_x"][i][None])
+        t, U, dUdt = c.get_state()
+        worst = max(worst, rel_inf(U, g["tf_U_after"][i][None]))
+        assert rel_inf(U, g["tf_U_after"][i][None]) <= TOL_U_REL
+        assert rel_inf(u, g["tf_u_after"][i][None]) <= TOL_U_REL
+        if BIT_EXACT[model]:
+            assert np.array_equal(U[0], g["tf_U_after"][i]) and np.array_equal(dUdt[0], g["tf_dUdt_after"][i])
+            assert np.array_equal(u[0], g["tf_u_after"][i])
+        assert t == float(g["tf_t"][i]) + c.dt
+    print(f"{po.MODEL_NAMES[model]}: worst teacher-forced rel dU = {worst:.3e}")
+    c.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_closed_loop_golden_batch_1000_steps(cg, model):
+    g = gold(model)
+    c, _ = make(cg, model, g["batch_x0"], g["batch_p"], g["batch_u0"])
+    worst = 0.0
+    for r in range(10):
+        c.step_closed_loop(100)
+        x, u = c.get_x(), c.get_u()
+        worst = max(worst, float(np.abs(x - g["batch_x_traj"][r]).max()))
+        check_pair(model, x, g["batch_x_traj"][r], f"x after {100 * (r + 1)} steps", TOL_X_ABS)
+        check_pair(model, u, g["batch_u_traj"][r], f"u after {100 * (r + 1)} steps", 1e-5)
+    _, U, dUdt = c.get_state()
+    check_pair(model, U, g["batch_U_fin"], "U after 1000 steps", 1e-5)
+    if BIT_EXACT[model]:
+        assert np.array_equal(dUdt, g["batch_dUdt_fin"])
+    code, ncol = c.get_status()
+    assert ((code >= 0) & (code <= 3)).all()
+    print(f"{po.MODEL_NAMES[model]}: closed-loop max|dx| over 1000 steps = {worst:.3e}")
+    c.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_closed_loop_shipped_ic_2000_steps(cg, model):
+    g, s = gold(model), po.SHIPPED[model]
+    c, _ = make(cg, model, np.array([s["x0"]]), np.array([s["p"]]), np.array(s["u0"]))
+    for r in range(20):
+        c.step_closed_loop(100)
+        check_pair(model, c.get_x()[0], g["shipped_x_traj"][r], f"x after {100 * (r + 1)}", TOL_X_ABS)
+        check_pair(model, c.get_u()[0], g["shipped_u_traj"][r], f"u after {100 * (r + 1)}", 1e-5)
+    c.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_seeded_batch_against_oracle(cg, oracle_best, model):
+    """257 instances (ragged: not a multiple of the warp or CTA size), 1000 closed-loop steps."""
+    n = 257
+    x0, p, u0 = po.synthetic_batch(model, n, seed=4242)
+    want = oracle_best.run_closed_loop(model, x0, p, u0, 1000, rec_stride=250, want_U=True,
+                                       n_threads=os.cpu_count() or 4)
+    c, _ = make(cg, model, x0, p, u0)
+    for r in range(4):
+        c.step_closed_loop(250)
+        check_pair(model, c.get_x(), want["x_traj"][r], f"x after {250 * (r + 1)}", TOL_X_ABS)
+    t, U, dUdt = c.get_state()
+    check_pair(model, U, want["U_fin"], "U", 1e-5)
+    check_pair(model, dUdt, want["dUdt_fin"], "dUdt", 1e-2)
+    assert abs(t - 1000 * c.dt) < 1e-9
+    c.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_host_control_api_like_reference_main(cg, oracle_best, model):
+    """The reference's main loop: u = control(x) with HOST buffers, then the plant step on the host."""
+    n, steps = 40, 60
+    x0, p, u0 = po.synthetic_batch(model, n, seed=99)
+    want = oracle_best.run_closed_loop(model, x0, p, u0, steps, want_U=True)
+    c, _ = make(cg, model, x0, p, u0)
+    x = x0.copy()
+    for _ in range(steps):
+        u = c.control(x)
+        for i in range(n):
+            oracle_best.plant_step(model, x[i], u[i])
+    check_pair(model, x, want["x_fin"], "x", TOL_X_ABS)
+    check_pair(model, c.get_state()[1], want["U_fin"], "U", 1e-7)
+    c.close()
+
+
+def test_time_varying_reference_trajectory(cg, oracle_best):
+    """set_ptau with a full per-stage reference (cgmres.hpp:36-39), SURVEY 8f row 2."""
+    model, n = po.MSD, 33
+    dm = oracle_best.dims(model)
+    x0, p, u0 = po.synthetic_batch(model, n, seed=5)
+    ramp = np.linspace(0.0, 0.3, dm.dv + 1)[None, :, None]
+    pfull = np.ascontiguousarray((p[:, None, :] + ramp).reshape(n, -1))
+    want = oracle_best.run_closed_loop(model, x0, pfull, u0, 200, p_full=True, want_U=True)
+    c, _ = make(cg, model, x0, pfull, u0, ptau_full=True)
+    c.step_closed_loop(200)
+    assert np.array_equal(c.get_x(), want["x_fin"])
+    assert np.array_equal(c.get_state()[1], want["U_fin"])
+    c.close()
+
+
+def test_exit_paths_match_oracle_on_long_msd_run(cg, oracle_port):
+    """Early convergence (one column dropped), rho0<tol stale-dUdt returns: SURVEY 0-3/0-4.
+    The shipped msd run hits both after ~step 5000; compare the per-step exit path and the state."""
+    model, s = po.MSD, po.SHIPPED[po.MSD]
+    steps = 9000
+    ctl = oracle_port.controller(model)
+    ctl.set_ptau_repeat(s["p"])
+    x = np.array(s["x0"])
+    ctl.init_u0_newton(s["u0"], x, s["p"], 10)
+    c, _ = make(cg, model, np.array([s["x0"]]), np.array([s["p"]]), np.array(s["u0"]))
+    seen = set()
+    for step in range(steps):
+        u = ctl.control(x)
+        oracle_port.plant_step(model, x, u)
+        c.step_closed_loop(1)
+        if step % 50 == 0 or step > steps - 300:
+            code, ncol = c.get_status()
+            assert (int(code[0]), int(ncol[0])) == ctl.last_status(), step
+            seen.add(int(code[0]))
+    assert np.array_equal(c.get_x()[0], x)
+    assert np.array_equal(c.get_state()[1][0], ctl.get_state()[1])
+    print("exit paths seen:", sorted(seen))
+
+
+def test_breakdown_path_reports_status_and_keeps_dUdt(cg, oracle_port):
+    """A badly posed semiactive instance breaks down; the reference printf()s and returns with
+    dUdt stale.  The GPU must report EXIT_BREAKDOWN and produce the same numbers."""
+    model = po.SEMIACTIVE
+    x0 = np.array([[2.0, 0.5], [2.0, 0.0], [1.0, -0.5], [2.5, 0.45]])
+    u0 = np.array(po.SHIPPED[model]["u0"])
+    c, _ = make(cg, model, x0, np.zeros((4, 0)), u0)
+    ctls, xs = [], x0.copy()
+    for i in range(4):
+        k = oracle_port.controller(model)
+        k.init_u0_newton(u0, x0[i], [0.0], 10)
+        ctls.append(k)
+    codes = set()
+    for step in range(400):
+        c.step_closed_loop(1)
+        code, ncol = c.get_status()
+        for i in range(4):
+            u = ctls[i].control(xs[i])
+            oracle_port.plant_step(model, xs[i], u)
+            assert (int(code[i]), int(ncol[i])) == ctls[i].last_status(), (step, i)
+            codes.add(int(code[i]))
+        if not np.isfinite(xs).all():
+            break
+    got = c.get_x()
+    assert np.array_equal(np.nan_to_num(got, nan=1e300), np.nan_to_num(xs, nan=1e300))
+    print("semiactive exit codes seen:", sorted(codes))
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 64, 65])
+def test_ragged_and_empty_batches(cg, oracle_best, n):
+    model = po.SEMIACTIVE
+    x0, p, u0 = po.synthetic_batch(model, n, seed=3)
+    c, _ = make(cg, model, x0, p, u0)
+    c.step_closed_loop(5)
+    x = c.get_x()
+    assert x.shape == (n, 2)
+    if n:
+        want = oracle_best.run_closed_loop(model, x0, p, u0, 5)
+        assert np.array_equal(x, want["x_fin"])
+    c.close()
+
+
+def test_full_size_batch_is_shard_invariant(cg, oracle_best):
+    """BASELINE config 2 size (65,536 msd instances): instances are independent, so any instance of the big
+    batch must equal the same instance run alone / in a small batch (and the oracle), bit for bit."""
+    model, n, steps = po.MSD, 65536, 12
+    x0, p, u0 = po.synthetic_batch(model, n, seed=2024)
+    c, _ = make(cg, model, x0, p, u0)
+    c.step_closed_loop(steps)
+    x_big = c.get_x()
+    _, U_big, _ = c.get_state(want_dUdt=False)
+    c.close()
+    assert np.isfinite(x_big).all()
+    idx = np.r_[0:48, 32760:32776, n - 48:n]
+    want = oracle_best.run_closed_loop(model, x0[idx], p[idx], u0, steps, want_U=True, n_threads=os.cpu_count() or 4)
+    assert np.array_equal(x_big[idx], want["x_fin"])
+    assert np.array_equal(U_big[idx], want["U_fin"])
+    # shard g of a G-way split == the same rows of the single-GPU run
+    lo, hi = n // 8 * 3, n // 8 * 3 + 200
+    c2, _ = make(cg, model, x0[lo:hi], p[lo:hi], u0)
+    c2.step_closed_loop(steps)
+    assert np.array_equal(c2.get_x(), x_big[lo:hi])
+    c2.close()
+
+
+def test_error_behaviour(cg):
+    with pytest.raises(cg.CgmresB200Error):
+        cg.BatchedCgmres(99, 4)
+    with pytest.raises(cg.CgmresB200Error):
+        cg.BatchedCgmres(cg.MSD, 4, device=12345)
+    with pytest.raises(cg.CgmresB200Error):
+        cg.BatchedCgmres(cg.MSD, -1)
