@@ -195,3 +195,10 @@ def launch_count() -> int:
 
 def device_count() -> int:
     return int(lib().cgmres_b200_device_count())
+
+
+def measure_fp64_peak(device: int = 0, use_fma: bool = True) -> float:
+    """Measured FP64 vector peak in TFLOP/s (DFMA = 2 flop; use_fma=False: separate DMUL+DADD)."""
+    v = C.c_double()
+    check(lib().cgmres_b200_measure_fp64_peak(device, int(use_fma), C.byref(v), None))
+    return float(v.value)

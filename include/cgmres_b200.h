@@ -126,6 +126,11 @@ int cgmres_b200_get_status(cgmres_b200_handle h, int32_t* status);
 /* kernels launched by this library in this process so far (for the benchmark's launch accounting) */
 int64_t cgmres_b200_launch_count(void);
 
+/* FP64 vector-pipe peak of `device`, measured with a register-resident chain microbenchmark: use_fma=1 counts
+ * DFMA as 2 flop, use_fma=0 issues separate DMUL+DADD (the ceiling of the exact mode).  The roofline denominator
+ * of the benchmark (MEASURED_PEAKS.json has no FP64 entry). sm_clock_mhz (may be NULL) = the device's nominal clock. */
+int cgmres_b200_measure_fp64_peak(int device, int use_fma, double* tflops, double* sm_clock_mhz);
+
 #ifdef __cplusplus
 }
 #endif
