@@ -200,7 +200,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     x0, p = x0_all[rank * n:(rank + 1) * n], p_all[rank * n:(rank + 1) * n]
 
     ctl = cg.BatchedCgmres(model_id, n, device=local_rank, mode=mode)
-    stream = torch.cuda.current_stream()
+    # the kernels are launched on this (non-default) stream and the CUDA events are recorded on the same one
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctl.set_stream(stream.cuda_stream)
     ctl.set_ptau_repeat(p)
     ctl.init_u0(u0)
