@@ -196,8 +196,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     mode = cg.MODE_FAST if args.mode == "fast" else cg.MODE_EXACT
     n = args.instances or INSTANCES_PER_GPU[model]
     # every rank owns a disjoint shard of one global seeded batch: rank r gets instances [r*n, (r+1)*n)
+    from cgmres_cpp_b200.sharding import aggregate_updates_per_second, max_over_ranks, weak_scaling_range
+
+    lo, hi = weak_scaling_range(n, world, rank)
     x0_all, p_all, u0 = po.synthetic_batch(model_id, n * world, seed=12345)
-    x0, p = x0_all[rank * n:(rank + 1) * n], p_all[rank * n:(rank + 1) * n]
+    x0, p = x0_all[lo:hi], p_all[lo:hi]
 
     ctl = cg.BatchedCgmres(model_id, n, device=local_rank, mode=mode)
     # the kernels are launched on this (non-default) stream and the CUDA events are recorded on the same one
@@ -258,17 +261,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     barrier()
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------------------
-    tt = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
+    total_ms_max, e2e_ms_max = max_over_ranks([total_ms, e2e_s * 1e3], dist, device="cuda")
     ok = torch.tensor([1.0 if finite else 0.0], device="cuda")
     if dist is not None:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 
     if rank == 0:
-        updates = n * world * args.steps
-        value = updates / (total_ms_max * 1e-3)
+        value = aggregate_updates_per_second(n, world, args.steps, total_ms_max)
         launch_ms = statistics.mean(per_launch_ms)
         p50_ms = statistics.median(per_launch_ms)
         peak_fma = cg.measure_fp64_peak(local_rank, True)

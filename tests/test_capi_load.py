@@ -62,3 +62,34 @@ def test_product_never_imports_the_oracle():
         p = os.path.join(ROOT, "include", f)
         if os.path.isfile(p):
             assert "oracle" not in open(p).read().lower(), f
+
+
+def test_cpp_dropin_header_compiles_with_host_compiler(built, tmp_path):
+    """include/cgmres.hpp + the per-example model.hpp/simulator.hpp names compile as plain C++ (no nvcc) and link
+    against the C-ABI library: what a maintainer of the reference's main.cpp would build."""
+    import subprocess
+
+    src = tmp_path / "main.cpp"
+    src.write_text("""
+#include "cgmres.hpp"
+#include "mass_spring_damper/model.hpp"
+#include "mass_spring_damper/simulator.hpp"
+#include "multiple_controller/model2.hpp"
+#include "multiple_controller/simulator1.hpp"
+static_assert(Cgmres<Model>::dim_x == 4 && Cgmres<Model>::dim_u == 6 && Cgmres<Model>::dv == 50, "msd dims");
+static_assert(Cgmres<Model2>::dim_u == 3 && Cgmres<Model2>::dv == 25, "arm dims");
+static_assert(Simulator::t_end == 20 && Simulator1::t_end == 10, "t_end");
+int main() {
+  double x[4] = {2, 2, 0, 0}, u[6] = {0, 0, 10, 10, 5e-4, 5e-4}, d[4];
+  Simulator::dxdt(d, x, u);              // host-side use of the same functor the kernels inline
+  if (d[2] != -2.0 + 2.0) return 2;      // -(k1*k2)/m1*x0 + k2/m1*x1 = -2 + 2
+  try { Cgmres<Model> c; c.control(u, x); } catch (const std::exception&) { return 0; }  // no GPU here: must throw
+  return 0;
+}
+""")
+    exe = tmp_path / "main"
+    lib_dir = os.path.join(ROOT, "cgmres_cpp_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-L", lib_dir,
+                        "-lcgmres_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0

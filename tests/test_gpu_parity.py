@@ -272,3 +272,27 @@ def test_error_behaviour(cg):
         cg.BatchedCgmres(cg.MSD, 4, device=12345)
     with pytest.raises(cg.CgmresB200Error):
         cg.BatchedCgmres(cg.MSD, -1)
+
+
+@pytest.mark.parametrize("how", ["host", "device"])
+def test_cpp_dropin_example_reproduces_reference_text_output(cg, oracle_best, tmp_path, how):
+    """examples/closed_loop.cpp = the reference's main.cpp on include/cgmres.hpp; its "%f" log of the shipped
+    mass_spring_damper run must equal the reference's own <example>_x.txt / _u.txt line for line."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "closed_loop")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "cgmres_cpp_b200", "csrc")], check=True)
+    steps = 400
+    r = subprocess.run([exe, "mass_spring_damper", "3", how, str(steps)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("Elapsed time = ")
+    s = po.SHIPPED[po.MSD]
+    want = oracle_best.run_closed_loop(po.MSD, [s["x0"]], [s["p"]], s["u0"], steps, rec_stride=1)
+    for name, traj in (("x", want["x_traj"][:, 0]), ("u", want["u_traj"][:, 0])):
+        lines = (tmp_path / f"mass_spring_damper_{name}.txt").read_text().splitlines()
+        assert len(lines) == steps
+        for i in (0, 1, 57, steps - 1):
+            ref_line = "%f" % (0.001 * i) + "".join("\t%f" % v for v in traj[i])
+            assert lines[i] == ref_line, (name, i)
