@@ -112,7 +112,7 @@ struct cgmres_b200_controller {
     if ((rc = dalloc(&ptau, l * (size_t)ptau_rows_full()))) return rc;
     if ((rc = dalloc(&F1, l * Lz))) return rc;
     if ((rc = dalloc(&V, l * Lz * (size_t)(mi->k_max + 1)))) return rc;
-    if ((rc = dalloc(&xtau, l * (size_t)mi->dim_x * (size_t)(mi->dv > 1 ? mi->dv - 1 : 1)))) return rc;
+    if ((rc = dalloc(&xtau, 3 * l * (size_t)mi->dim_x * (size_t)(mi->dv > 1 ? mi->dv - 1 : 1)))) return rc;  // 3 planes
     if ((rc = dalloc(&u_out, l * mi->dim_u))) return rc;
     if ((rc = dalloc(&status, l))) return rc;
     if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;

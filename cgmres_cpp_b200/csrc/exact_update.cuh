@@ -27,6 +27,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "cgmres_b200/models.hpp"
 #include "kernel_args.h"
 
@@ -53,17 +55,26 @@ struct Ws {
   static __host__ __device__ constexpr int r(int i, int j) { return R + j * (j + 1) / 2 + i; }
 };
 
-enum SweepKind { SWEEP_F1 = 0, SWEEP_B = 1, SWEEP_R0 = 2, SWEEP_W = 3 };
+enum SweepKind { SWEEP_W = 3 };
 
-// One evaluation of F (cgmres.hpp:113-162) with its caller's element-wise post-processing fused in.
-//   KIND = SWEEP_F1: inputs U           ; out[j]  = F                              (cgmres.hpp:88)
-//          SWEEP_B : inputs U           ; out[j]  = ((F*c1) - F1[j])*inv_h         (cgmres.hpp:91-96)
-//          SWEEP_R0: inputs U + h*pert  ; out[j]  = out[j] - ((F - F1[j])*inv_h)   (gmres.hpp:33-34)
-//          SWEEP_W : inputs U + h*(pert*ps) ; out[j] = (F - F1[j])*inv_h           (gmres.hpp:48, cgmres.hpp:164-175)
-template <class M, bool PFULL, int KIND>
-__device__ __forceinline__ void sweep(const ExactArgs& a, const int64_t n, const double* x0, const double dtau,
-                                      const double* __restrict__ pert, const double ps, double* __restrict__ out,
-                                      const double* pconst) {
+// Runs body(j0, integral_constant<int,NB>) over [0,L) in batches of B (tail batch of L%B): inside a batch the
+// caller first issues all its loads and then does the (order-preserving) arithmetic, which gives the memory
+// system B x streams independent requests per thread instead of one dependent load per element.
+template <int L, int B, class Body>
+__device__ __forceinline__ void for_batches(Body&& body) {
+  constexpr int full = L / B, tail = L % B;
+  for (int b = 0; b < full; b++) body(b * B, std::integral_constant<int, B>());
+  if (tail > 0) body(full * B, std::integral_constant<int, (tail > 0 ? tail : 1)>());
+}
+
+// One evaluation of F (cgmres.hpp:113-162) at U + h*v_k with the Jacobian-vector post-processing fused in:
+//   inputs  u = (pert*ps)*h + U   (v_k[j] = r_k[j]*(1/||r_k||), gmres.hpp:44,67; cgmres.hpp:168-169)
+//   out[j]  = (F - F1[j])*inv_h   (cgmres.hpp:173-174)
+// The next stage's inputs are requested before the current stage's dependent arithmetic starts.
+template <class M, bool PFULL>
+__device__ __forceinline__ void sweep_w(const ExactArgs& a, const int64_t n, const double* x0, const double dtau,
+                                        const double* __restrict__ pert, const double ps, double* __restrict__ out,
+                                        const double* pconst) {
   using S = Sz<M>;
   constexpr int nx = S::nx, nu = S::nu, np = S::np, dv = S::dv;
   const int64_t ld = a.ld;
@@ -73,22 +84,21 @@ __device__ __forceinline__ void sweep(const ExactArgs& a, const int64_t n, const
   const double* __restrict__ pt = a.ptau + n;
   constexpr double hh = M::h;
   constexpr double inv_h = 1.0 / M::h;
-  constexpr double c1 = (1 - M::zeta * M::h);
 
-  auto load_u = [&](double* u, int i) {
+  auto load_raw = [&](double* uu, double* vv, int i) {
 #pragma unroll
     for (int j = 0; j < nu; j++) {
       const int64_t o = (int64_t)(i * nu + j) * ld;
-      double uu = U[o];
-      if (KIND == SWEEP_R0) {
-        double v = pert[o] * hh;  // mul(U_buf, dUdt, h)
-        uu = v + uu;              // add(U_buf, U_buf, U)
-      } else if (KIND == SWEEP_W) {
-        double v = pert[o] * ps;  // v_k[j] = r_k[j]*(1/||r_k||)  (gmres.hpp:44,67)
-        v = v * hh;
-        uu = v + uu;
-      }
-      u[j] = uu;
+      uu[j] = U[o];
+      vv[j] = pert[o];
+    }
+  };
+  auto combine = [&](double* u, const double* uu, const double* vv) {
+#pragma unroll
+    for (int j = 0; j < nu; j++) {
+      double v = vv[j] * ps;
+      v = v * hh;
+      u[j] = v + uu[j];
     }
   };
   auto load_p = [&](double* p, int i) {
@@ -96,15 +106,17 @@ __device__ __forceinline__ void sweep(const ExactArgs& a, const int64_t n, const
     for (int j = 0; j < np; j++) p[j] = PFULL ? pt[(int64_t)(i * np + j) * ld] : pconst[j];
   };
 
-  double xc[nx], u[nu], p[S::np1];
+  double xc[nx], u[nu], p[S::np1], uu[nu], vv[nu];
 #pragma unroll
   for (int j = 0; j < nx; j++) xc[j] = x0[j];
 
   // forward Euler rollout (cgmres.hpp:132-140); xtau[1..dv-1] go to scratch, xtau[0]=x0 and xtau[dv] stay in registers
+  load_raw(uu, vv, 0);
   for (int i = 0; i < dv; i++) {
     double f[nx];
-    load_u(u, i);
+    combine(u, uu, vv);
     load_p(p, i);
+    if (i + 1 < dv) load_raw(uu, vv, i + 1);
     M::dxdt(f, xc, u, p);
 #pragma unroll
     for (int j = 0; j < nx; j++) {
@@ -118,11 +130,13 @@ __device__ __forceinline__ void sweep(const ExactArgs& a, const int64_t n, const
   }
 
   // terminal costate (cgmres.hpp:145) and backward sweep (cgmres.hpp:146-153) with dHdu (cgmres.hpp:156-161) fused in
-  double lmd[nx];
+  double lmd[nx], xi[nx], f1[nu];
   load_p(p, dv);
   M::dPhidx(lmd, xc, p);
-  for (int i = dv - 1; i >= 0; i--) {
-    double xi[nx], hu[nu], hx[nx];
+  auto load_back = [&](int i) {
+    load_raw(uu, vv, i);
+#pragma unroll
+    for (int j = 0; j < nu; j++) f1[j] = F1[(int64_t)(i * nu + j) * ld];
     if (i > 0) {
 #pragma unroll
       for (int j = 0; j < nx; j++) xi[j] = xt[(int64_t)((i - 1) * nx + j) * ld];
@@ -130,34 +144,171 @@ __device__ __forceinline__ void sweep(const ExactArgs& a, const int64_t n, const
 #pragma unroll
       for (int j = 0; j < nx; j++) xi[j] = x0[j];
     }
-    load_u(u, i);
+  };
+  load_back(dv - 1);
+  for (int i = dv - 1; i >= 0; i--) {
+    double xs[nx], fs[nu], hu[nu], hx[nx];
+    combine(u, uu, vv);
+#pragma unroll
+    for (int j = 0; j < nx; j++) xs[j] = xi[j];
+#pragma unroll
+    for (int j = 0; j < nu; j++) fs[j] = f1[j];
     load_p(p, i);
-    M::dHdu(hu, xi, u, p, lmd);
+    if (i > 0) load_back(i - 1);
+    M::dHdu(hu, xs, u, p, lmd);
 #pragma unroll
     for (int j = 0; j < nu; j++) {
-      const int64_t o = (int64_t)(i * nu + j) * ld;
-      if (KIND == SWEEP_F1) {
-        out[o] = hu[j];
-      } else if (KIND == SWEEP_B) {
-        double b = hu[j] * c1;
-        b = b - F1[o];
-        out[o] = b * inv_h;
-      } else if (KIND == SWEEP_R0) {
-        double ax = hu[j] - F1[o];
-        ax = ax * inv_h;
-        out[o] = out[o] - ax;
-      } else {
-        double ax = hu[j] - F1[o];
-        out[o] = ax * inv_h;
-      }
+      const double ax = hu[j] - fs[j];
+      out[(int64_t)(i * nu + j) * ld] = ax * inv_h;
     }
     if (i > 0) {  // ltau[0] is never read by the reference (cgmres.hpp:160 uses ltau[i+1] only)
-      M::dHdx(hx, xi, u, p, lmd);
+      M::dHdx(hx, xs, u, p, lmd);
 #pragma unroll
       for (int j = 0; j < nx; j++) {
         double m = hx[j] * dtau;
         lmd[j] = m + lmd[j];
       }
+    }
+  }
+}
+
+// The three F evaluations that do not depend on the Krylov iteration, in ONE pair of horizon sweeps:
+//   A: F(U, x+dx*h, t+h)            -> F1           (cgmres.hpp:88)
+//   B: F(U, x, t)                   -> b            (cgmres.hpp:91-96), never stored
+//   C: F(U+h*dUdt, x+dx*h, t+h)     -> r0 = b - Ax  (gmres.hpp:33-34, cgmres.hpp:164-175), stored to column 0
+// U and dUdt are read once per direction instead of three times and b / F1 are consumed from registers.
+template <class M, bool PFULL>
+__device__ __forceinline__ void sweep_first3(const ExactArgs& a, const int64_t n, const double* x, const double* xh,
+                                             double* __restrict__ r0out, const double* pconst) {
+  using S = Sz<M>;
+  constexpr int nx = S::nx, nu = S::nu, np = S::np, dv = S::dv;
+  const int64_t ld = a.ld;
+  const double* __restrict__ U = a.U + n;
+  const double* __restrict__ dU = a.dUdt + n;
+  double* __restrict__ F1 = a.F1 + n;
+  const int64_t plane = (int64_t)nx * (dv > 1 ? dv - 1 : 1) * ld;
+  double* __restrict__ xtA = a.xtau + n;
+  double* __restrict__ xtB = xtA + plane;
+  double* __restrict__ xtC = xtB + plane;
+  const double* __restrict__ pt = a.ptau + n;
+  const double dth = a.dtau_th, dt0 = a.dtau_t;
+  constexpr double hh = M::h;
+  constexpr double inv_h = 1.0 / M::h;
+  constexpr double c1 = (1 - M::zeta * M::h);
+
+  auto load_raw = [&](double* uu, double* vv, int i) {
+#pragma unroll
+    for (int j = 0; j < nu; j++) {
+      const int64_t o = (int64_t)(i * nu + j) * ld;
+      uu[j] = U[o];
+      vv[j] = dU[o];
+    }
+  };
+  auto combine = [&](double* uc, const double* uu, const double* vv) {
+#pragma unroll
+    for (int j = 0; j < nu; j++) {
+      double v = vv[j] * hh;  // mul(U_buf, dUdt, h); add(U_buf, U_buf, U)
+      uc[j] = v + uu[j];
+    }
+  };
+  auto load_p = [&](double* p, int i) {
+#pragma unroll
+    for (int j = 0; j < np; j++) p[j] = PFULL ? pt[(int64_t)(i * np + j) * ld] : pconst[j];
+  };
+  auto euler = [&](double* xc, const double* u, const double* p, double dtau) {
+    double f[nx];
+    M::dxdt(f, xc, u, p);
+#pragma unroll
+    for (int j = 0; j < nx; j++) {
+      double m = f[j] * dtau;
+      xc[j] = m + xc[j];
+    }
+  };
+
+  double xa[nx], xb[nx], xc3[nx], ua[nu], uc[nu], uu[nu], vv[nu], p[S::np1];
+#pragma unroll
+  for (int j = 0; j < nx; j++) {
+    xa[j] = xh[j];
+    xb[j] = x[j];
+    xc3[j] = xh[j];
+  }
+  load_raw(uu, vv, 0);
+  for (int i = 0; i < dv; i++) {
+#pragma unroll
+    for (int j = 0; j < nu; j++) ua[j] = uu[j];
+    combine(uc, uu, vv);
+    load_p(p, i);
+    if (i + 1 < dv) load_raw(uu, vv, i + 1);
+    euler(xa, ua, p, dth);
+    euler(xb, ua, p, dt0);
+    euler(xc3, uc, p, dth);
+    if (i + 1 < dv) {
+#pragma unroll
+      for (int j = 0; j < nx; j++) {
+        const int64_t o = (int64_t)(i * nx + j) * ld;
+        xtA[o] = xa[j];
+        xtB[o] = xb[j];
+        xtC[o] = xc3[j];
+      }
+    }
+  }
+
+  auto costate = [&](double* l, const double* xs, const double* u, const double* p, double dtau) {
+    double hx[nx];
+    M::dHdx(hx, xs, u, p, l);
+#pragma unroll
+    for (int j = 0; j < nx; j++) {
+      double m = hx[j] * dtau;
+      l[j] = m + l[j];
+    }
+  };
+  double la[nx], lb[nx], lc[nx];
+  load_p(p, dv);
+  M::dPhidx(la, xa, p);
+  M::dPhidx(lb, xb, p);
+  M::dPhidx(lc, xc3, p);
+  load_raw(uu, vv, dv - 1);
+  for (int i = dv - 1; i >= 0; i--) {
+    double sa[nx], sb[nx], sc[nx], ha[nu], hb[nu], hc[nu];
+    if (i > 0) {  // rollout states of this stage: written a few hundred instructions ago, served by L1/L2
+#pragma unroll
+      for (int j = 0; j < nx; j++) {
+        const int64_t o = (int64_t)((i - 1) * nx + j) * ld;
+        sa[j] = xtA[o];
+        sb[j] = xtB[o];
+        sc[j] = xtC[o];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < nx; j++) {
+        sa[j] = xh[j];
+        sb[j] = x[j];
+        sc[j] = xh[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < nu; j++) ua[j] = uu[j];
+    combine(uc, uu, vv);
+    load_p(p, i);
+    if (i > 0) load_raw(uu, vv, i - 1);
+    M::dHdu(ha, sa, ua, p, la);
+    M::dHdu(hb, sb, ua, p, lb);
+    M::dHdu(hc, sc, uc, p, lc);
+#pragma unroll
+    for (int j = 0; j < nu; j++) {
+      const int64_t o = (int64_t)(i * nu + j) * ld;
+      F1[o] = ha[j];
+      double b = hb[j] * c1;  // (F*(1-zeta*h) - F1)*(1/h), three roundings (cgmres.hpp:94-96)
+      b = b - ha[j];
+      b = b * inv_h;
+      double ax = hc[j] - ha[j];  // (F(U+h*dUdt) - F1)*(1/h) (cgmres.hpp:173-174)
+      ax = ax * inv_h;
+      r0out[o] = b - ax;  // gmres.hpp:34
+    }
+    if (i > 0) {
+      costate(la, sa, ua, p, dth);
+      costate(lb, sb, ua, p, dt0);
+      costate(lc, sc, uc, p, dth);
     }
   }
 }
@@ -168,6 +319,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
   using S = Sz<M>;
   using W = Ws<M>;
   constexpr int nx = S::nx, nu = S::nu, np = S::np, L = S::L, km = S::km;
+  constexpr int B2 = 12, B3 = 10;  // elements per load batch in passes with 2 / 3+ streams
   const int64_t ld = a.ld;
   const int bs = blockDim.x;
 #define WS(e) sm[(e) * bs]
@@ -195,9 +347,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
   double* V = a.V + n;
   auto col = [&](int k) { return V + (int64_t)k * L * ld; };
 
-  sweep<M, PFULL, SWEEP_F1>(a, n, xh, a.dtau_th, nullptr, 0.0, a.F1 + n, pc);  // F(U, x+dx*h, t+h)
-  sweep<M, PFULL, SWEEP_B>(a, n, x, a.dtau_t, nullptr, 0.0, col(0), pc);       // b, staged in column 0
-  sweep<M, PFULL, SWEEP_R0>(a, n, xh, a.dtau_th, a.dUdt + n, 0.0, col(0), pc); // r0 = b - A*dUdt
+  sweep_first3<M, PFULL>(a, n, x, xh, col(0), pc);  // F1, b and r0 = b - A*dUdt in one pair of sweeps
 
   int code = EXIT_FULL;
   int ncol = 0;
@@ -207,11 +357,14 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
   {
     double s = 0;
     const double* r0 = col(0);
-#pragma unroll 4
-    for (int j = 0; j < L; j++) {
-      const double v = r0[(int64_t)j * ld];
-      s += v * v;
-    }
+    for_batches<L, B2 + B3>([&](int j0, auto nb) {
+      constexpr int NB = decltype(nb)::value;
+      double v[NB];
+#pragma unroll
+      for (int q = 0; q < NB; q++) v[q] = r0[(int64_t)(j0 + q) * ld];
+#pragma unroll
+      for (int q = 0; q < NB; q++) s += v[q] * v[q];
+    });
     const double rho0 = sqrt(s);
     WS(W::RHO + 0) = rho0;
     if (rho0 < M::tol) {  // gmres.hpp:39-41: silent return, dUdt keeps its old value
@@ -226,18 +379,27 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
     int k = 0;
     for (; k < km; k++) {
       double* w = col(k + 1);
-      sweep<M, PFULL, SWEEP_W>(a, n, xh, a.dtau_th, col(k), WS(W::VS + k), w, pc);  // w = A v_k (gmres.hpp:48)
+      sweep_w<M, PFULL>(a, n, xh, a.dtau_th, col(k), WS(W::VS + k), w, pc);  // w = A v_k (gmres.hpp:48)
 
       // modified Gram-Schmidt (gmres.hpp:52-58); h_ik kept in HC[i]
       {
         const double* r0 = col(0);
         const double s0 = WS(W::VS + 0);
         double acc = 0;
-#pragma unroll 4
-        for (int j = 0; j < L; j++) {
-          const double v = r0[(int64_t)j * ld] * s0;
-          acc += v * w[(int64_t)j * ld];
-        }
+        for_batches<L, B2>([&](int j0, auto nb) {
+          constexpr int NB = decltype(nb)::value;
+          double rv[NB], wv[NB];
+#pragma unroll
+          for (int q = 0; q < NB; q++) {
+            rv[q] = r0[(int64_t)(j0 + q) * ld];
+            wv[q] = w[(int64_t)(j0 + q) * ld];
+          }
+#pragma unroll
+          for (int q = 0; q < NB; q++) {
+            const double v = rv[q] * s0;
+            acc += v * wv[q];
+          }
+        });
         WS(W::HC + 0) = acc;
       }
       for (int i = 0; i < k; i++) {  // w -= v_i*h_i fused with h_{i+1} = <v_{i+1}, w>
@@ -245,16 +407,26 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
         const double* rn = col(i + 1);
         const double si = WS(W::VS + i), sn = WS(W::VS + i + 1), hi = WS(W::HC + i);
         double acc = 0;
-#pragma unroll 4
-        for (int j = 0; j < L; j++) {
-          const int64_t o = (int64_t)j * ld;
-          const double vi = ri[o] * si;
-          const double t = vi * hi;
-          const double wj = w[o] - t;
-          w[o] = wj;
-          const double vn = rn[o] * sn;
-          acc += vn * wj;
-        }
+        for_batches<L, B3>([&](int j0, auto nb) {
+          constexpr int NB = decltype(nb)::value;
+          double av[NB], bv[NB], wv[NB];
+#pragma unroll
+          for (int q = 0; q < NB; q++) {
+            const int64_t o = (int64_t)(j0 + q) * ld;
+            av[q] = ri[o];
+            bv[q] = rn[o];
+            wv[q] = w[o];
+          }
+#pragma unroll
+          for (int q = 0; q < NB; q++) {
+            const double vi = av[q] * si;
+            const double t = vi * hi;
+            const double wj = wv[q] - t;
+            w[(int64_t)(j0 + q) * ld] = wj;
+            const double vn = bv[q] * sn;
+            acc += vn * wj;
+          }
+        });
         WS(W::HC + i + 1) = acc;
       }
       double hn;
@@ -262,15 +434,24 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
         const double* rk = col(k);
         const double sk = WS(W::VS + k), hk = WS(W::HC + k);
         double acc = 0;
-#pragma unroll 4
-        for (int j = 0; j < L; j++) {
-          const int64_t o = (int64_t)j * ld;
-          const double vk = rk[o] * sk;
-          const double t = vk * hk;
-          const double wj = w[o] - t;
-          w[o] = wj;
-          acc += wj * wj;
-        }
+        for_batches<L, B2>([&](int j0, auto nb) {
+          constexpr int NB = decltype(nb)::value;
+          double av[NB], wv[NB];
+#pragma unroll
+          for (int q = 0; q < NB; q++) {
+            const int64_t o = (int64_t)(j0 + q) * ld;
+            av[q] = rk[o];
+            wv[q] = w[o];
+          }
+#pragma unroll
+          for (int q = 0; q < NB; q++) {
+            const double vk = av[q] * sk;
+            const double t = vk * hk;
+            const double wj = wv[q] - t;
+            w[(int64_t)(j0 + q) * ld] = wj;
+            acc += wj * wj;
+          }
+        });
         hn = sqrt(acc);
       }
       if (fabs(hn) < DBL_EPSILON) {  // gmres.hpp:63-65 "Breakdown": return without touching dUdt
@@ -335,25 +516,38 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
     }
     double* __restrict__ Up = a.U + n;
     double* __restrict__ dU = a.dUdt + n;
-#pragma unroll 2
-    for (int j = 0; j < L; j++) {
-      const int64_t o = (int64_t)j * ld;
-      double d = dU[o];
-      if (solve) {
-        double s = 0.0;
+    constexpr int BF = 4;
+    for_batches<L, BF>([&](int j0, auto nb) {
+      constexpr int NB = decltype(nb)::value;
+      double dv_[NB], uv[NB], cv[NB][km];
 #pragma unroll
-        for (int c = 0; c < km; c++) {
-          if (c < ncol) {
-            const double v = V[(int64_t)c * L * ld + o] * sc[c];
-            s += v * y[c];
-          }
-        }
-        d = d + s;
-        dU[o] = d;
+      for (int q = 0; q < NB; q++) {
+        const int64_t o = (int64_t)(j0 + q) * ld;
+        dv_[q] = dU[o];
+        uv[q] = Up[o];
+#pragma unroll
+        for (int c = 0; c < km; c++) cv[q][c] = (solve && c < ncol) ? V[(int64_t)c * L * ld + o] : 0.0;
       }
-      const double inc = d * M::dt;
-      Up[o] = Up[o] + inc;
-    }
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int64_t o = (int64_t)(j0 + q) * ld;
+        double d = dv_[q];
+        if (solve) {
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < km; c++) {
+            if (c < ncol) {
+              const double v = cv[q][c] * sc[c];
+              s += v * y[c];
+            }
+          }
+          d = d + s;
+          dU[o] = d;
+        }
+        const double inc = d * M::dt;
+        Up[o] = uv[q] + inc;
+      }
+    });
   }
 
   // u = U[0:dim_u] (cgmres.hpp:109): re-read this thread's own stores
@@ -377,7 +571,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
 }
 
 template <class M, class Sim, bool PFULL>
-__global__ void __launch_bounds__(64) control_kernel(const ExactArgs a) {
+__global__ void __maxnreg__(144) control_kernel(const ExactArgs a) {
   extern __shared__ double sm_ws[];
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= a.n) return;

@@ -32,7 +32,7 @@ struct ExactArgs {
   const double* ptau;  // [dim_p][ld] (repeat) or [(dv+1)*dim_p][ld] (full)   (cgmres.hpp:200)
   double* F1;          // [L][ld]          F(U, x+dx*h, t+h)    (cgmres.hpp:202)
   double* V;           // [(k_max+1)*L][ld] un-normalised Krylov basis (gmres.hpp:11)
-  double* xtau;        // [dim_x*(dv-1)][ld] rollout scratch    (cgmres.hpp:116)
+  double* xtau;        // [3][dim_x*(dv-1)][ld] rollout scratch, one plane per fused trajectory (cgmres.hpp:116)
   double* u_out;       // [dim_u][ld]      u = U[0:dim_u]       (cgmres.hpp:109)
   int32_t* status;     // [ld]
   double dtau_t, dtau_th;  // get_dtau(t), get_dtau(t+h) evaluated on the host (cgmres.hpp:32-34)
