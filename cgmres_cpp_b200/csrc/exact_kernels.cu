@@ -14,6 +14,9 @@ cudaError_t launch_control_t(bool pfull, const ExactArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
   const size_t smem = sizeof(double) * exact::Ws<M>::COUNT * kBlock;
   if (grid == 0) return cudaSuccess;
+  // Shared-memory carve-out is left to the driver on purpose: 6 resident CTAs need 157 KB for the per-thread
+  // GMRES scalars and the remaining ~70 KB of L1 serves the rollout-scratch re-reads; forcing the maximum
+  // carve-out measured 13 % slower (profiles/README.md).
   if (pfull)
     exact::control_kernel<M, Sim, true><<<grid, kBlock, smem, s>>>(a);
   else

@@ -32,6 +32,19 @@
 #include "cgmres_b200/models.hpp"
 #include "kernel_args.h"
 
+// Tuning knobs (GPU sweep in profiles/README.md).  The register file is split per SM sub-partition
+// (16,384 registers each), so resident warps per SM = 4*floor(16384/(32*regs)): 128 registers -> 16 warps,
+// 129..168 -> 12 warps.  168 keeps the kernels free of spills at 12 warps (6 CTAs) per SM.
+#ifndef CG_MAXREG
+#define CG_MAXREG 168
+#endif
+#ifndef CG_B2
+#define CG_B2 16  // elements per load batch, passes with 2 streams
+#define CG_B3 12  // passes with 3+ streams
+#define CG_BN 24  // norm pass (1 stream)
+#define CG_BF 5   // final pass (7 streams)
+#endif
+
 namespace cgmres_b200 {
 namespace exact {
 
@@ -319,7 +332,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
   using S = Sz<M>;
   using W = Ws<M>;
   constexpr int nx = S::nx, nu = S::nu, np = S::np, L = S::L, km = S::km;
-  constexpr int B2 = 12, B3 = 10;  // elements per load batch in passes with 2 / 3+ streams
+  constexpr int B2 = CG_B2, B3 = CG_B3;  // elements per load batch in passes with 2 / 3+ streams
   const int64_t ld = a.ld;
   const int bs = blockDim.x;
 #define WS(e) sm[(e) * bs]
@@ -357,7 +370,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
   {
     double s = 0;
     const double* r0 = col(0);
-    for_batches<L, B2 + B3>([&](int j0, auto nb) {
+    for_batches<L, CG_BN>([&](int j0, auto nb) {
       constexpr int NB = decltype(nb)::value;
       double v[NB];
 #pragma unroll
@@ -516,7 +529,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
     }
     double* __restrict__ Up = a.U + n;
     double* __restrict__ dU = a.dUdt + n;
-    constexpr int BF = 4;
+    constexpr int BF = CG_BF;
     for_batches<L, BF>([&](int j0, auto nb) {
       constexpr int NB = decltype(nb)::value;
       double dv_[NB], uv[NB], cv[NB][km];
@@ -571,7 +584,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
 }
 
 template <class M, class Sim, bool PFULL>
-__global__ void __maxnreg__(144) control_kernel(const ExactArgs a) {
+__global__ void __maxnreg__(CG_MAXREG) control_kernel(const ExactArgs a) {
   extern __shared__ double sm_ws[];
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= a.n) return;
