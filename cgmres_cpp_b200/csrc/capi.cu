@@ -78,6 +78,7 @@ struct cgmres_b200_controller {
   double* stage = nullptr;  // instance-major staging, grown on demand
   size_t stage_doubles = 0;
 
+  bool soa() const { return mode == CGMRES_B200_MODE_EXACT; }  // exact: [element][instance]; on-chip kernels: [instance][element]
   int L() const { return mi->L(); }
   int ptau_rows_full() const { return (mi->dv + 1) * mi->dim_p; }
 
@@ -106,6 +107,16 @@ struct cgmres_b200_controller {
   int allocate() {
     const size_t l = (size_t)ld, Lz = (size_t)L();
     int rc;
+    if (!soa()) {  // on-chip kernels: only the persistent state lives in HBM, instance-major like the ABI
+      if ((rc = dalloc(&x, l * mi->dim_x))) return rc;
+      if ((rc = dalloc(&U, l * Lz))) return rc;
+      if ((rc = dalloc(&dUdt, l * Lz))) return rc;
+      if ((rc = dalloc(&ptau, l * (size_t)ptau_rows_full()))) return rc;
+      if ((rc = dalloc(&u_out, l * mi->dim_u))) return rc;
+      if ((rc = dalloc(&status, l))) return rc;
+      if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;
+      return 0;
+    }
     if ((rc = dalloc(&x, l * mi->dim_x))) return rc;
     if ((rc = dalloc(&U, l * Lz))) return rc;
     if ((rc = dalloc(&dUdt, l * Lz))) return rc;  // zero: the de-facto contract of cgmres.hpp:14
@@ -137,7 +148,26 @@ struct cgmres_b200_controller {
 
   // one update for every instance; plant=1 also advances x (closed loop on device)
   int launch_update(int plant) {
-    if (mode != CGMRES_B200_MODE_EXACT) return fail(CGMRES_B200_ENOTIMPL, "fast mode not built for this model");
+    if (!soa()) {
+      FastArgs f;
+      f.n = n;
+      f.x = x;
+      f.U = U;
+      f.dUdt = dUdt;
+      f.ptau = ptau;
+      f.u_out = u_out;
+      f.status = status;
+      f.dtau_t = dtau(t);
+      f.dtau_th = dtau(t + mi->h);
+      f.plant = plant;
+      if (mode == CGMRES_B200_MODE_FAST)
+        CU(fast_launch_control(model, ptau_full, f, stream));
+      else
+        CU(onchip_exact_launch_control(model, ptau_full, f, stream));
+      g_launches++;
+      t = t + mi->dt;
+      return 0;
+    }
     ExactArgs a;
     a.n = n;
     a.ld = ld;
@@ -160,8 +190,13 @@ struct cgmres_b200_controller {
   }
 
   // host instance-major -> device SoA rows
-  int upload_rows(const double* host, double* soa, int rows) {
+  int upload_rows(const double* host, double* dst, int rows) {
     if (rows == 0 || n == 0) return 0;
+    if (!soa()) {
+      CU(cudaMemcpyAsync(dst, host, sizeof(double) * (size_t)n * rows, cudaMemcpyHostToDevice, stream));
+      return 0;
+    }
+    double* soa = dst;
     int rc = ensure_stage((size_t)n * rows);
     if (rc) return rc;
     CU(cudaMemcpyAsync(stage, host, sizeof(double) * (size_t)n * rows, cudaMemcpyHostToDevice, stream));
@@ -169,8 +204,14 @@ struct cgmres_b200_controller {
     g_launches++;
     return 0;
   }
-  int download_rows(double* host, const double* soa, int rows) {
+  int download_rows(double* host, const double* src, int rows) {
     if (rows == 0 || n == 0) return 0;
+    if (!soa()) {
+      CU(cudaMemcpyAsync(host, src, sizeof(double) * (size_t)n * rows, cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      return 0;
+    }
+    const double* soa = src;
     int rc = ensure_stage((size_t)n * rows);
     if (rc) return rc;
     CU(launch_soa_to_aos(soa, stage, n, rows, ld, stream));
@@ -233,8 +274,8 @@ int cgmres_b200_create(int model, int64_t n, int device, int mode, cgmres_b200_h
   const ModelInfo* mi = model_info(model);
   if (!mi) return fail(CGMRES_B200_EINVAL, "unknown model id");
   if (n < 0) return fail(CGMRES_B200_EINVAL, "negative instance count");
-  if (mode != CGMRES_B200_MODE_EXACT && mode != CGMRES_B200_MODE_FAST) return fail(CGMRES_B200_EINVAL, "unknown mode");
-  if (mode == CGMRES_B200_MODE_FAST) return fail(CGMRES_B200_ENOTIMPL, "fast mode not built for this model");
+  if (mode != CGMRES_B200_MODE_EXACT && mode != CGMRES_B200_MODE_FAST && mode != CGMRES_B200_MODE_ONCHIP_EXACT)
+    return fail(CGMRES_B200_EINVAL, "unknown mode");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -335,7 +376,10 @@ int cgmres_b200_init_u0(cgmres_b200_handle h, const double* u0) {
   int rc = h->ensure_stage((size_t)h->n * nu);
   if (rc) return rc;
   CU(cudaMemcpyAsync(h->stage, u0, sizeof(double) * (size_t)h->n * nu, cudaMemcpyHostToDevice, h->stream));
-  CU(launch_broadcast_rows(h->stage, h->U, h->n, nu, h->mi->dv, h->ld, h->stream));
+  if (h->soa())
+    CU(launch_broadcast_rows(h->stage, h->U, h->n, nu, h->mi->dv, h->ld, h->stream));
+  else
+    CU(launch_broadcast_inst(h->stage, h->U, h->n, nu, h->mi->dv, h->stream));
   g_launches++;
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -355,7 +399,8 @@ int cgmres_b200_init_u0_newton(cgmres_b200_handle h, double* u0, const double* x
   CU(cudaMemcpyAsync(d_u, u0, sizeof(double) * n * nu, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(d_x, x0, sizeof(double) * n * nx, cudaMemcpyHostToDevice, h->stream));
   if (np > 0) CU(cudaMemcpyAsync(d_p, p0, sizeof(double) * n * np, cudaMemcpyHostToDevice, h->stream));
-  CU(exact_launch_newton(h->model, h->n, h->ld, d_u, d_x, d_p, np, n_loop, h->U, h->stream));
+  CU(exact_launch_newton(h->model, h->n, h->soa() ? h->ld : 1, h->soa() ? 1 : (int64_t)h->L(), d_u, d_x, d_p, np,
+                         n_loop, h->U, h->stream));
   g_launches++;
   CU(cudaMemcpyAsync(u0, d_u, sizeof(double) * n * nu, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -366,6 +411,15 @@ int cgmres_b200_control_dev(cgmres_b200_handle h, double* u_dev, const double* x
   CHECK_H(h);
   ON_DEVICE(h);
   if (!u_dev || !x_dev) return fail(CGMRES_B200_EINVAL, "null device pointer");
+  if (!h->soa()) {  // instance-major state == ABI layout: plain device copies
+    const size_t n = (size_t)h->n;
+    if (n == 0) return 0;
+    CU(cudaMemcpyAsync(h->x, x_dev, sizeof(double) * n * h->mi->dim_x, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = h->launch_update(0);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(u_dev, h->u_out, sizeof(double) * n * h->mi->dim_u, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+  }
   CU(launch_aos_to_soa(x_dev, h->x, h->n, h->mi->dim_x, h->ld, h->stream));
   g_launches++;
   int rc = h->launch_update(0);

@@ -628,10 +628,12 @@ __device__ __forceinline__ void linsolve(double* vec, double* mat) {
   }
 }
 
-// u0[n][nu] (instance-major, in/out), x0[n][nx], p0[n][p_stride] (first dim_p entries used); fills U rows with the result
+// u0[n][nu] (instance-major, in/out), x0[n][nx], p0[n][p_stride] (first dim_p entries used); fills U with the
+// result: element e of instance n at U[e*es + n*is]
 template <class M>
-__global__ void newton_init_kernel(int64_t n_inst, int64_t ld, double* __restrict__ u0, const double* __restrict__ x0,
-                                   const double* __restrict__ p0, int p_stride, int n_loop, double* __restrict__ U) {
+__global__ void newton_init_kernel(int64_t n_inst, int64_t es, int64_t is, double* __restrict__ u0,
+                                   const double* __restrict__ x0, const double* __restrict__ p0, int p_stride,
+                                   int n_loop, double* __restrict__ U) {
   using S = Sz<M>;
   constexpr int nx = S::nx, nu = S::nu, np = S::np, dv = S::dv;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -649,7 +651,7 @@ __global__ void newton_init_kernel(int64_t n_inst, int64_t ld, double* __restric
   }
   for (int j = 0; j < nu; j++) u0[n * nu + j] = u[j];
   for (int i = 0; i < dv; i++)
-    for (int j = 0; j < nu; j++) U[(int64_t)(i * nu + j) * ld + n] = u[j];
+    for (int j = 0; j < nu; j++) U[(int64_t)(i * nu + j) * es + n * is] = u[j];
 }
 
 }  // namespace exact

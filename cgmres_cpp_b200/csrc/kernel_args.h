@@ -39,10 +39,32 @@ struct ExactArgs {
   int plant;               // 1: also advance x by one Euler plant step
 };
 
+// Instance-major device state of the on-chip ("fast") kernels: the layout of the C ABI itself, every instance's
+// vectors contiguous (U[n][L], x[n][dim_x], ...), so a warp loads its instance with coalesced 256-byte requests.
+struct FastArgs {
+  int64_t n;
+  double* x;           // [n][dim_x]
+  double* U;           // [n][L]
+  double* dUdt;        // [n][L]
+  const double* ptau;  // [n][dim_p] (repeat) or [n][(dv+1)*dim_p] (full)
+  double* u_out;       // [n][dim_u]
+  int32_t* status;     // [n]
+  double dtau_t, dtau_th;
+  int plant;
+};
+
+// on-chip kernels: fast_kernels.cu (FMA, shuffle reductions) and their sequential-sum, no-FMA twin compiled in
+// exact_kernels.cu (bit-identical to the reference; verification build of the same kernel)
+cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
+cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
+int fast_instances_per_cta(int model);
+
 // exact mode (exact_kernels.cu)
 cudaError_t exact_launch_control(int model, bool ptau_full, const ExactArgs& a, cudaStream_t s);
-cudaError_t exact_launch_newton(int model, int64_t n, int64_t ld, double* u0_aos, const double* x0_aos,
-                                const double* p0_aos, int p_stride, int n_loop, double* U_soa, cudaStream_t s);
+// U element e of instance i is written to U[e*elem_stride + i*inst_stride] (SoA: ld,1; instance-major: 1,L)
+cudaError_t exact_launch_newton(int model, int64_t n, int64_t elem_stride, int64_t inst_stride, double* u0_aos,
+                                const double* x0_aos, const double* p0_aos, int p_stride, int n_loop, double* U,
+                                cudaStream_t s);
 size_t exact_control_smem_bytes(int model, int block);
 
 // layout kernels (layout.cu): instance-major host layout <-> structure of arrays
@@ -52,5 +74,7 @@ cudaError_t launch_soa_to_aos(const double* soa, double* aos, int64_t n, int row
 // soa[(i*rows_per + j)][n] = aos[n][j] for i in 0..reps-1 (init_u0 / set_ptau_repeat broadcasts)
 cudaError_t launch_broadcast_rows(const double* aos, double* soa, int64_t n, int rows_per, int reps, int64_t ld,
                                   cudaStream_t s);
+// dst[n][i*rows_per + j] = aos[n][j] for i in 0..reps-1 (instance-major destination)
+cudaError_t launch_broadcast_inst(const double* aos, double* dst, int64_t n, int rows_per, int reps, cudaStream_t s);
 
 }  // namespace cgmres_b200

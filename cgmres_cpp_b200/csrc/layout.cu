@@ -54,7 +54,25 @@ __global__ void broadcast_rows_kernel(const double* __restrict__ aos, double* __
     for (int i = 0; i < reps; i++) soa[(int64_t)(i * rows_per + j) * ld + nn] = v;
   }
 }
+__global__ void broadcast_inst_kernel(const double* __restrict__ aos, double* __restrict__ dst, int64_t n,
+                                      int rows_per, int reps) {
+  const int64_t total = n * (int64_t)rows_per * reps;
+  const int64_t per = (int64_t)rows_per * reps;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t nn = t / per;
+    const int j = (int)((t % per) % rows_per);
+    dst[t] = aos[nn * rows_per + j];
+  }
+}
 }  // namespace
+
+cudaError_t launch_broadcast_inst(const double* aos, double* dst, int64_t n, int rows_per, int reps, cudaStream_t s) {
+  if (n == 0 || rows_per == 0 || reps == 0) return cudaSuccess;
+  const int64_t total = n * (int64_t)rows_per * reps;
+  const unsigned grid = (unsigned)((total + 255) / 256 > 65535 * 16 ? 65535 * 16 : (total + 255) / 256);
+  broadcast_inst_kernel<<<grid, 256, 0, s>>>(aos, dst, n, rows_per, reps);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_aos_to_soa(const double* aos, double* soa, int64_t n, int rows, int64_t ld, cudaStream_t s) {
   if (n == 0 || rows == 0) return cudaSuccess;

@@ -1,0 +1,154 @@
+"""GPU parity tests of the on-chip control-update kernel (cgmres_cpp_b200/csrc/fast_update.cuh):
+
+  MODE_ONCHIP_EXACT  the kernel with the reference's sequential sums and no FMA -> bit-identical to the oracle
+                     (mass_spring_damper, semiactive_damper), which verifies its data movement and control flow;
+  MODE_FAST          the same kernel with FMA contraction and shuffle reductions -> the north-star tolerances:
+                     |dU|_inf/|U|_inf <= 1e-9 per (teacher-forced) update, max|dx| <= 1e-6 over 1000 closed-loop steps.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from test_gpu_parity import BIT_EXACT, MODELS, TOL_U_REL, TOL_X_ABS, gold, make, rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cg(built):
+    import cgmres_cpp_b200 as m
+
+    if m.device_count() == 0:
+        pytest.fail("GPU test selected but no CUDA device is visible (no CPU fallback exists)")
+    return m
+
+
+# ---------------------------------------------------------------- on-chip kernel, exact arithmetic
+@pytest.mark.parametrize("model", MODELS)
+def test_onchip_exact_golden_batch_1000_steps(cg, model):
+    g = gold(model)
+    c, un = make(cg, model, g["batch_x0"], g["batch_p"], g["batch_u0"], mode=cg.MODE_ONCHIP_EXACT)
+    for r in range(10):
+        c.step_closed_loop(100)
+        x, u = c.get_x(), c.get_u()
+        if BIT_EXACT[model]:
+            assert np.array_equal(x, g["batch_x_traj"][r]), (r, np.abs(x - g["batch_x_traj"][r]).max())
+            assert np.array_equal(u, g["batch_u_traj"][r])
+        else:
+            assert np.abs(x - g["batch_x_traj"][r]).max() <= TOL_X_ABS
+    _, U, dUdt = c.get_state()
+    if BIT_EXACT[model]:
+        assert np.array_equal(U, g["batch_U_fin"]) and np.array_equal(dUdt, g["batch_dUdt_fin"])
+    c.close()
+
+
+@pytest.mark.parametrize("model", [po.MSD, po.SEMIACTIVE])
+@pytest.mark.parametrize("n", [1, 7, 45])
+def test_onchip_exact_ragged_batches_match_oracle(cg, oracle_best, model, n):
+    """n not a multiple of the instances-per-CTA group (partial last CTA)."""
+    x0, p, u0 = po.synthetic_batch(model, n, seed=31 + n)
+    want = oracle_best.run_closed_loop(model, x0, p, u0, 120, want_U=True)
+    c, _ = make(cg, model, x0, p, u0, mode=cg.MODE_ONCHIP_EXACT)
+    c.step_closed_loop(120)
+    assert np.array_equal(c.get_x(), want["x_fin"])
+    t, U, dUdt = c.get_state()
+    assert np.array_equal(U, want["U_fin"]) and np.array_equal(dUdt, want["dUdt_fin"])
+    c.close()
+
+
+def test_onchip_exact_exit_paths_on_long_msd_run(cg, oracle_port):
+    model, s = po.MSD, po.SHIPPED[po.MSD]
+    steps = 9000
+    ctl = oracle_port.controller(model)
+    ctl.set_ptau_repeat(s["p"])
+    x = np.array(s["x0"])
+    ctl.init_u0_newton(s["u0"], x, s["p"], 10)
+    c, _ = make(cg, model, np.array([s["x0"]]), np.array([s["p"]]), np.array(s["u0"]), mode=cg.MODE_ONCHIP_EXACT)
+    seen = set()
+    for step in range(steps):
+        u = ctl.control(x)
+        oracle_port.plant_step(model, x, u)
+        c.step_closed_loop(1)
+        if step % 50 == 0 or step > steps - 300:
+            code, ncol = c.get_status()
+            assert (int(code[0]), int(ncol[0])) == ctl.last_status(), step
+            seen.add(int(code[0]))
+    assert np.array_equal(c.get_x()[0], x)
+    assert np.array_equal(c.get_state()[1][0], ctl.get_state()[1])
+    assert {0, 1, 2} <= seen
+
+
+def test_onchip_exact_time_varying_reference_and_host_api(cg, oracle_best):
+    model, n = po.MSD, 13
+    dm = oracle_best.dims(model)
+    x0, p, u0 = po.synthetic_batch(model, n, seed=5)
+    ramp = np.linspace(0.0, 0.3, dm.dv + 1)[None, :, None]
+    pfull = np.ascontiguousarray((p[:, None, :] + ramp).reshape(n, -1))
+    want = oracle_best.run_closed_loop(model, x0, pfull, u0, 60, p_full=True, want_U=True)
+    c, _ = make(cg, model, x0, pfull, u0, mode=cg.MODE_ONCHIP_EXACT, ptau_full=True)
+    x = x0.copy()
+    for _ in range(60):  # host-buffer API like the reference's main()
+        u = c.control(x)
+        for i in range(n):
+            oracle_best.plant_step(model, x[i], u[i])
+    assert np.array_equal(x, want["x_fin"])
+    assert np.array_equal(c.get_state()[1], want["U_fin"])
+    c.close()
+
+
+# ---------------------------------------------------------------- fast mode, tolerance bars
+@pytest.mark.parametrize("model", MODELS)
+def test_fast_teacher_forced_update(cg, model):
+    g, s = gold(model), po.SHIPPED[model]
+    c = cg.BatchedCgmres(model, 1, mode=cg.MODE_FAST)
+    if c.dim_p:
+        c.set_ptau_repeat([s["p"]])
+    worst = 0.0
+    for i in range(len(g["tf_steps"])):
+        c.set_state(float(g["tf_t"][i]), g["tf_U"][i][None], g["tf_dUdt"][i][None])
+        u = c.control(g["tf_x"][i][None])
+        _, U, _ = c.get_state(want_dUdt=False)
+        worst = max(worst, rel_inf(U, g["tf_U_after"][i][None]), rel_inf(u, g["tf_u_after"][i][None]))
+    print(f"fast {po.MODEL_NAMES[model]}: worst teacher-forced rel dU = {worst:.3e}")
+    assert worst <= TOL_U_REL
+    c.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_fast_closed_loop_1000_steps(cg, oracle_best, model):
+    g = gold(model)
+    n = 264  # 8 golden instances + 256 seeded ones
+    x0s, ps, u0 = po.synthetic_batch(model, n - 8, seed=4242)
+    x0 = np.concatenate([g["batch_x0"], x0s])
+    p = np.concatenate([g["batch_p"], ps]) if ps.shape[1] else np.zeros((n, 0))
+    want = oracle_best.run_closed_loop(model, x0, p, u0, 1000, rec_stride=100, n_threads=os.cpu_count() or 4)
+    assert np.array_equal(want["x_traj"][:, :8], g["batch_x_traj"])  # the oracle reproduces the golden rows
+    c, _ = make(cg, model, x0, p, u0, mode=cg.MODE_FAST)
+    worst = 0.0
+    for r in range(10):
+        c.step_closed_loop(100)
+        worst = max(worst, float(np.abs(c.get_x() - want["x_traj"][r]).max()))
+    print(f"fast {po.MODEL_NAMES[model]}: closed-loop max|dx| over 1000 steps, {n} instances = {worst:.3e}")
+    assert worst <= TOL_X_ABS
+    code, _ = c.get_status()
+    assert ((code >= 0) & (code <= 3)).all()
+    c.close()
+
+
+def test_fast_full_size_batch_shard_invariance(cg):
+    """65,536 instances: every instance of the big batch equals the same instance run in a small batch, bit for
+    bit (no cross-instance arithmetic exists), and stays finite."""
+    model, n, steps = po.MSD, 65536, 10
+    x0, p, u0 = po.synthetic_batch(model, n, seed=2024)
+    c, _ = make(cg, model, x0, p, u0, mode=cg.MODE_FAST)
+    c.step_closed_loop(steps)
+    x_big = c.get_x()
+    c.close()
+    assert np.isfinite(x_big).all()
+    lo, hi = 40000, 40123
+    c2, _ = make(cg, model, x0[lo:hi], p[lo:hi], u0, mode=cg.MODE_FAST)
+    c2.step_closed_loop(steps)
+    assert np.array_equal(c2.get_x(), x_big[lo:hi])
+    c2.close()
