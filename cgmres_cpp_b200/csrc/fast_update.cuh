@@ -30,7 +30,13 @@
 namespace cgmres_b200 {
 namespace fast {
 
-constexpr int kSmemBudget = 227 * 1024;
+constexpr int kSmemBudget = 227 * 1024 - 2048;  // leave the per-CTA reserved shared memory of up to 2 CTAs
+#ifndef CG_FAST_GCAP
+#define CG_FAST_GCAP 12  // max instances (= warps) per CTA
+#endif
+#ifndef CG_FAST_WARPS
+#define CG_FAST_WARPS 16  // max resident warps (= instances) per SM: 16 warps leave 128 registers per thread
+#endif
 
 template <class M>
 struct Lay {
@@ -40,8 +46,9 @@ struct Lay {
   static constexpr int XT = nx * (dv > 1 ? dv - 1 : 1);  // stored rollout states xtau[1..dv-1]
   static constexpr int Q = (L + 31) / 32;                // vector elements per lane
   // per-instance shared-memory block, offsets in doubles
-  static constexpr int oU = 0;            // U                      (cgmres.hpp:196)
-  static constexpr int oF1 = oU + L;      // F(U, x+dx*h, t+h)      (cgmres.hpp:202)
+  // (U itself is not kept on chip: it is re-read from global memory -- an L2 hit, the CTA touched it a few
+  //  microseconds earlier -- where U + h*v is formed and in the final update.)
+  static constexpr int oF1 = 0;           // U during the first evaluation, then F(U, x+dx*h, t+h) (cgmres.hpp:202)
   static constexpr int oX = oF1 + L;      // U + h*v  ->  w         (cgmres.hpp:168-174), products in EXACT_SUMS
   static constexpr int oV = oX + L;       // km basis columns r_0..r_{km-1}, un-normalised (gmres.hpp:11)
   static constexpr int oXT = oV + km * L; // rollout states xtau[1..dv-1] of the Arnoldi sweeps / trajectory A
@@ -50,7 +57,8 @@ struct Lay {
   static constexpr bool xt_alias = (XT <= L) && (km >= 5);
   static constexpr int oXTB = xt_alias ? oV + (km - 1) * L : oXT + XT;
   static constexpr int oXTC = xt_alias ? oV : oXT + 2 * XT;
-  static constexpr int oS = oXT + (xt_alias ? 1 : 3) * XT; // scalars
+  static constexpr int oLT = oXT + (xt_alias ? 1 : 3) * XT;  // costates ltau[1..dv] of the Arnoldi sweeps
+  static constexpr int oS = oLT + nx * dv;                   // scalars
   // scalar slots
   static constexpr int sR = 0;                         // packed upper triangle R(i,j), i<=j<km
   static constexpr int sG = sR + km * (km + 1) / 2;    // 3*km reflectors
@@ -69,36 +77,33 @@ struct Lay {
   static constexpr int G_fit = kSmemBudget / (stride * 8);
   // instances per CTA (one warp each): what fits in shared memory, capped at 12 warps so that every thread
   // can keep ~168 registers (the register file, not shared memory, bounds the small-L models)
-  static constexpr int G = G_fit > 12 ? 12 : G_fit;
+  static constexpr int G = G_fit > CG_FAST_GCAP ? CG_FAST_GCAP : G_fit;
+  // co-resident CTAs (they run out of phase, which overlaps one CTA's serial sweep with another's vector work):
+  // bounded by shared memory (G_fit instances per SM) and by CG_FAST_WARPS warps per SM (register budget)
+  static constexpr int inst_per_sm = G_fit > CG_FAST_WARPS ? CG_FAST_WARPS : G_fit;
+  static constexpr int ctas_per_sm = (inst_per_sm / G) < 1 ? 1 : (inst_per_sm / G);
   static constexpr int threads = 32 * G;
   static constexpr size_t smem_bytes = (size_t)G * stride * 8;
   static __host__ __device__ constexpr int r(int i, int j) { return sR + j * (j + 1) / 2 + i; }
 };
 
-// One horizon sweep for one instance, executed by ONE lane (cgmres.hpp:113-162).
-//   in[]  : stage inputs u_i (shared memory, L doubles)     out[]: dHdu per stage (may alias in[]: u_i is read
-//   xt[]  : rollout scratch plane                                   before out_i is written, same lane)
-//   MODE 0: out = F                                   (first three evaluations)
-//   MODE 1: out = (F - F1)*inv_h                      (Jacobian-vector product, cgmres.hpp:173-174)
-template <class M, int MODE>
-__device__ __forceinline__ void lane_sweep(const double* in, double* out, const double* f1, double* xt,
-                                           const double* x0, const double dtau, const double* pconst,
-                                           const double* pfull /* global [(dv+1)*np] or null */) {
+// Forward Euler rollout of one instance by ONE lane (cgmres.hpp:132-140): returns xtau[dv] in xc, stores
+// xtau[1..dv-1] to the scratch plane xt.
+template <class M>
+__device__ __forceinline__ void lane_rollout(const double* in, double* xt, const double* x0, const double dtau,
+                                             const double* pconst, const double* pfull, double* xc) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
-  constexpr double inv_h = 1.0 / M::h;
-  double xc[nx], u[nu], p[Y::np1];
-  auto load_p = [&](int i) {
-#pragma unroll
-    for (int j = 0; j < np; j++) p[j] = pfull ? pfull[i * np + j] : pconst[j];
-  };
+  double u[nu], p[Y::np1];
 #pragma unroll
   for (int j = 0; j < nx; j++) xc[j] = x0[j];
-  for (int i = 0; i < dv; i++) {  // forward Euler rollout, cgmres.hpp:132-140
+#pragma unroll 2
+  for (int i = 0; i < dv; i++) {
     double f[nx];
 #pragma unroll
     for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
-    load_p(i);
+#pragma unroll
+    for (int j = 0; j < np; j++) p[j] = pfull ? pfull[i * np + j] : pconst[j];
     M::dxdt(f, xc, u, p);
 #pragma unroll
     for (int j = 0; j < nx; j++) {
@@ -110,31 +115,32 @@ __device__ __forceinline__ void lane_sweep(const double* in, double* out, const 
       for (int j = 0; j < nx; j++) xt[i * nx + j] = xc[j];
     }
   }
-  double lmd[nx];
-  load_p(dv);
+}
+
+// Full sweep with dHdu inside (used for the three Krylov-independent evaluations, where 3 lanes per instance
+// are busy): out[i] = dHdu(x_i, u_i, p_i, lambda_{i+1})   (cgmres.hpp:113-162)
+template <class M>
+__device__ __forceinline__ void lane_sweep_full(const double* in, double* out, double* xt, const double* x0,
+                                                const double dtau, const double* pconst, const double* pfull) {
+  using Y = Lay<M>;
+  constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
+  double xc[nx], lmd[nx], u[nu], p[Y::np1];
+  lane_rollout<M>(in, xt, x0, dtau, pconst, pfull, xc);
+#pragma unroll
+  for (int j = 0; j < np; j++) p[j] = pfull ? pfull[dv * np + j] : pconst[j];
   M::dPhidx(lmd, xc, p);  // cgmres.hpp:145
-  for (int i = dv - 1; i >= 0; i--) {  // costate sweep with dHdu fused, cgmres.hpp:146-161
+#pragma unroll 2
+  for (int i = dv - 1; i >= 0; i--) {  // cgmres.hpp:146-161
     double xi[nx], hu[nu], hx[nx];
-    if (i > 0) {
 #pragma unroll
-      for (int j = 0; j < nx; j++) xi[j] = xt[(i - 1) * nx + j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < nx; j++) xi[j] = x0[j];
-    }
+    for (int j = 0; j < nx; j++) xi[j] = (i > 0) ? xt[(i - 1) * nx + j] : x0[j];
 #pragma unroll
     for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
-    load_p(i);
+#pragma unroll
+    for (int j = 0; j < np; j++) p[j] = pfull ? pfull[i * np + j] : pconst[j];
     M::dHdu(hu, xi, u, p, lmd);
 #pragma unroll
-    for (int j = 0; j < nu; j++) {
-      if (MODE == 0) {
-        out[i * nu + j] = hu[j];
-      } else {
-        double ax = hu[j] - f1[i * nu + j];
-        out[i * nu + j] = ax * inv_h;
-      }
-    }
+    for (int j = 0; j < nu; j++) out[i * nu + j] = hu[j];
     if (i > 0) {
       M::dHdx(hx, xi, u, p, lmd);
 #pragma unroll
@@ -142,6 +148,40 @@ __device__ __forceinline__ void lane_sweep(const double* in, double* out, const 
         double m = hx[j] * dtau;
         lmd[j] = m + lmd[j];
       }
+    }
+  }
+}
+
+// Arnoldi sweeps: the serial lane only runs the two recursions (rollout and costate) and leaves the costates
+// lt[i] = ltau[i+1], i = 0..dv-1; the stage-parallel dHdu (cgmres.hpp:156-161) is evaluated afterwards by the
+// owning warp, one stage per lane.  This takes ~40 % of the instructions off the serial critical path.
+template <class M>
+__device__ __forceinline__ void lane_sweep_costates(const double* in, double* xt, double* lt, const double* x0,
+                                                    const double dtau, const double* pconst, const double* pfull) {
+  using Y = Lay<M>;
+  constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
+  double xc[nx], lmd[nx], u[nu], p[Y::np1];
+  lane_rollout<M>(in, xt, x0, dtau, pconst, pfull, xc);
+#pragma unroll
+  for (int j = 0; j < np; j++) p[j] = pfull ? pfull[dv * np + j] : pconst[j];
+  M::dPhidx(lmd, xc, p);
+#pragma unroll
+  for (int j = 0; j < nx; j++) lt[(dv - 1) * nx + j] = lmd[j];
+#pragma unroll 2
+  for (int i = dv - 1; i > 0; i--) {
+    double xi[nx], hx[nx];
+#pragma unroll
+    for (int j = 0; j < nx; j++) xi[j] = xt[(i - 1) * nx + j];
+#pragma unroll
+    for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+#pragma unroll
+    for (int j = 0; j < np; j++) p[j] = pfull ? pfull[i * np + j] : pconst[j];
+    M::dHdx(hx, xi, u, p, lmd);
+#pragma unroll
+    for (int j = 0; j < nx; j++) {
+      double m = hx[j] * dtau;
+      lmd[j] = m + lmd[j];
+      lt[(i - 1) * nx + j] = lmd[j];
     }
   }
 }
@@ -154,7 +194,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // The kernel.  grid = ceil(n / G) CTAs of 32*G threads; dynamic shared memory = Lay<M>::smem_bytes.
 template <class M, class Sim, bool PFULL, bool EXACT_SUMS>
-__global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastArgs a) {
+__global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_kernel(const FastArgs a) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, L = Y::L, km = Y::km, Q = Y::Q, G = Y::G;
   constexpr double hh = M::h;
@@ -171,8 +211,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   auto col = [&](int k) { return blk + Y::oV + k * L; };
   auto inst_blk = [&](int g) { return sm + (size_t)g * Y::stride; };
 
-  // ---- phase 0: state in.  U -> smem, X = U + h*dUdt (input of the third trajectory), x, p(t) -------------
-  double dU[Q];  // this lane's slice of dUdt stays in registers until the final update
+  // ---- phase 0: state in.  U -> F1 area, X = U + h*dUdt (input of the third trajectory), x, p(t) ----------
   if (has) {
     const double* Ug = a.U + n * (int64_t)L;
     const double* dUg = a.dUdt + n * (int64_t)L;
@@ -181,9 +220,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
       const int j = lane + 32 * q;
       if (j < L) {
         const double uu = Ug[j];
-        dU[q] = dUg[j];
-        blk[Y::oU + j] = uu;
-        double v = dU[q] * hh;  // cgmres.hpp:168-169
+        blk[Y::oF1 + j] = uu;  // the F1 area holds U until F1 exists
+        double v = dUg[j] * hh;  // cgmres.hpp:168-169
         blk[Y::oX + j] = v + uu;
       }
     }
@@ -197,7 +235,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
 #pragma unroll
     for (int j = 0; j < nx; j++) x[j] = sc[Y::sX + j];
 #pragma unroll
-    for (int j = 0; j < nu; j++) u0[j] = blk[Y::oU + j];
+    for (int j = 0; j < nu; j++) u0[j] = blk[Y::oF1 + j];
 #pragma unroll
     for (int j = 0; j < np; j++) p0[j] = sc[Y::sP + j];
     M::dxdt(f, x, u0, p0);
@@ -217,8 +255,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
     const double* s = b + Y::oS;
     const double* pf = PFULL ? a.ptau + (n0 + g) * (int64_t)((M::dv + 1) * np) : nullptr;
     double* plane = b + (tr == 0 ? Y::oXT : (tr == 1 ? Y::oXTB : Y::oXTC));
-    lane_sweep<M, 0>(tr == 2 ? b + Y::oX : b + Y::oU, b + Y::oV + (1 + tr) * L, nullptr, plane,
-                     tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? a.dtau_t : a.dtau_th, s + Y::sP, pf);
+    lane_sweep_full<M>(tr == 2 ? b + Y::oX : b + Y::oF1, b + Y::oV + (1 + tr) * L, plane,
+                       tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? a.dtau_t : a.dtau_th, s + Y::sP, pf);
   }
   __syncthreads();
 
@@ -284,11 +322,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   if (has && lane == 0) sc[Y::sFLAG] = solving ? 0.0 : 1.0;
 
   // ---- Arnoldi iterations ------------------------------------------------------------------------------------
-  double R[km * (km + 1) / 2], gv[3 * km];
-#pragma unroll
-  for (int i = 0; i < km * (km + 1) / 2; i++) R[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 3 * km; i++) gv[i] = 0.0;
+  // R (packed triangle) and the reflectors are warp-uniform and touched a few times per iteration only: they
+  // live in this instance's shared-memory scalars (written by lane 0, read by all lanes after __syncwarp).
 
 #pragma unroll
   for (int k = 0; k < km; k++) {
@@ -300,7 +335,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         if (j < L) {
           double v = w[q] * vs[k];
           v = v * hh;
-          blk[Y::oX + j] = v + blk[Y::oU + j];
+          blk[Y::oX + j] = v + a.U[n * (int64_t)L + j];
         }
       }
     }
@@ -310,11 +345,33 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
       const double* s = b + Y::oS;
       if (s[Y::sFLAG] == 0.0) {
         const double* pf = PFULL ? a.ptau + (n0 + threadIdx.x) * (int64_t)((M::dv + 1) * np) : nullptr;
-        lane_sweep<M, 1>(b + Y::oX, b + Y::oX, b + Y::oF1, b + Y::oXT, s + Y::sXH, a.dtau_th, s + Y::sP, pf);
+        lane_sweep_costates<M>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, a.dtau_th, s + Y::sP, pf);
       }
     }
     __syncthreads();
     if (solving) {
+      // stage-parallel dHdu (cgmres.hpp:156-161) and (F - F1)*inv_h (cgmres.hpp:173-174), one stage per lane;
+      // w_i overwrites u_i in X (same lane reads before it writes)
+      const double* pf = PFULL ? a.ptau + n * (int64_t)((M::dv + 1) * np) : nullptr;
+      for (int i = lane; i < M::dv; i += 32) {
+        double xi[nx], u[nu], p[Y::np1], lm[nx], hu[nu];
+#pragma unroll
+        for (int j = 0; j < nx; j++) {
+          xi[j] = (i > 0) ? blk[Y::oXT + (i - 1) * nx + j] : sc[Y::sXH + j];
+          lm[j] = blk[Y::oLT + i * nx + j];
+        }
+#pragma unroll
+        for (int j = 0; j < nu; j++) u[j] = blk[Y::oX + i * nu + j];
+#pragma unroll
+        for (int j = 0; j < np; j++) p[j] = PFULL ? pf[i * np + j] : sc[Y::sP + j];
+        M::dHdu(hu, xi, u, p, lm);
+#pragma unroll
+        for (int j = 0; j < nu; j++) {
+          double ax = hu[j] - blk[Y::oF1 + i * nu + j];
+          blk[Y::oX + i * nu + j] = ax * inv_h;
+        }
+      }
+      __syncwarp();
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int j = lane + 32 * q;
@@ -389,7 +446,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
       // stored reflectors on the new column (gmres.hpp:71-77), new reflector (78-85), residual (88-90)
 #pragma unroll
       for (int i = 0; i < k; i++) {
-        const double g0 = gv[3 * i], g1 = gv[3 * i + 1], g2 = gv[3 * i + 2];
+        const double g0 = sc[Y::sG + 3 * i], g1 = sc[Y::sG + 3 * i + 1], g2 = sc[Y::sG + 3 * i + 2];
         const double buf = (g0 * hc[i] + g1 * hc[i + 1]) * g2;
         hc[i] = hc[i] - buf * g0;
         hc[i + 1] = hc[i + 1] - buf * g1;
@@ -400,16 +457,21 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         const double buf = -sg * sqrt((0.0 + ha * ha) + hb * hb);
         const double g0 = ha - buf, g1 = hb;
         const double g2 = 2.0 / ((0.0 + g0 * g0) + g1 * g1);
-        gv[3 * k] = g0;
-        gv[3 * k + 1] = g1;
-        gv[3 * k + 2] = g2;
+        if (lane == 0) {
+          sc[Y::sG + 3 * k] = g0;
+          sc[Y::sG + 3 * k + 1] = g1;
+          sc[Y::sG + 3 * k + 2] = g2;
+        }
         hc[k] = buf;
         const double rb = g0 * rho[k] * g2;
         rho[k] = rho[k] - rb * g0;
         rho[k + 1] = -rb * g1;
       }
+      if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i <= k; i++) R[Y::r(i, k)] = hc[i];
+        for (int i = 0; i <= k; i++) sc[Y::r(i, k)] = hc[i];
+      }
+      __syncwarp();
       ncol = k + 1;
       if (fabs(rho[k + 1]) < M::tol) {  // gmres.hpp:93-95: break with k not incremented
         code = EXIT_CONVERGED;
@@ -429,8 +491,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         double ri = rho[i];
 #pragma unroll
         for (int j = km - 1; j > i; j--)
-          if (j < ncol) ri -= R[Y::r(i, j)] * rho[j];
-        ri /= R[Y::r(i, i)];
+          if (j < ncol) ri -= sc[Y::r(i, j)] * rho[j];
+        ri /= sc[Y::r(i, i)];
         rho[i] = ri;
       }
     }
@@ -442,7 +504,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
     for (int q = 0; q < Q; q++) {
       const int j = lane + 32 * q;
       if (j < L) {
-        double d = dU[q];
+        double d = dUg[j];  // second (L2-resident) read instead of 2*Q live registers through the whole solve
         if (apply) {
           double s = 0.0;
 #pragma unroll
@@ -456,9 +518,9 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           dUg[j] = d;
         }
         const double inc = d * M::dt;
-        const double un = blk[Y::oU + j] + inc;
+        const double un = Ug[j] + inc;
         Ug[j] = un;
-        if (j < nu) blk[Y::oU + j] = un;  // keep u = U[0:dim_u] for the epilogue
+        if (j < nu) blk[Y::oX + j] = un;  // park u = U[0:dim_u] for the epilogue (X is free now)
       }
     }
     __syncwarp();
@@ -466,7 +528,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
       double x[nx], u0[nu];
 #pragma unroll
       for (int j = 0; j < nu; j++) {
-        u0[j] = blk[Y::oU + j];
+        u0[j] = blk[Y::oX + j];
         a.u_out[n * nu + j] = u0[j];  // cgmres.hpp:109
       }
       if (a.plant) {  // <example>/main.cpp:74-76
