@@ -1,25 +1,30 @@
-// fast_update.cuh -- "fast" build mode: the whole control update of a group of G instances runs out of
-// shared memory and registers of ONE CTA; HBM only sees the algorithmic minimum (read U, dUdt, x, p; write
-// U, dUdt, x, u: 9.7 KB per mass_spring_damper update instead of the ~250 KB the streaming exact kernel moves).
+// fast_update.cuh -- "fast" build mode: the whole control update of a group of G instances runs out of the
+// on-chip memories of ONE CTA; HBM only sees the algorithmic minimum (read U, dUdt, x, p; write U, dUdt, x, u:
+// ~9 KB per mass_spring_damper update instead of the ~250 KB the streaming exact kernel moves).
 //
 // Mapping (north star items 2-4):
 //   * warp g of the CTA owns instance g for all vector work: lane l holds elements l, l+32, ... of the length-L
 //     vectors (the working vector w stays in registers through a whole Gram-Schmidt sweep), dot products and
 //     norms are butterfly shuffle reductions, the Hessenberg / Householder / back-substitution scalars
 //     (gmres.hpp:71-107) are warp-uniform registers + a few shared-memory words.
+//   * the Krylov basis (gmres.hpp:11; 12 KB per mass_spring_damper instance, the largest object by far) lives in
+//     TENSOR MEMORY: each lane's slice of a basis vector is a few 32-bit TMEM columns of that lane, written once
+//     with tcgen05.st and read back with tcgen05.ld.  TMEM is used purely as 256 KB of extra per-lane private
+//     storage (no MMA anywhere); that frees shared memory for 16 instead of 10 resident instances per SM, and
+//     resident instances per SM is what bounds this latency-chain-dominated kernel.
 //   * the horizon sweeps (cgmres.hpp:113-162) are serial over dv and only dim_x wide, and lanes of a warp
 //     cannot run different formulas without divergence, so they are TRANSPOSED: in the sweep phases lane l of
-//     the first warp(s) runs the rollout + costate + dHdu of instance l (three trajectories per instance for
-//     the fused F(U,x+dx*h,t+h) / F(U,x,t) / F(U+h*dUdt,x+dx*h,t+h) evaluation) straight out of the
-//     instances' shared-memory blocks; the per-instance block stride is odd in 8-byte words so those
-//     lane-per-instance accesses are bank-conflict free.
-//   * Krylov basis (gmres.hpp:11), U, F_dxh_h, the U+h*v buffer and the rollout states never leave the SM.
+//     the first warp(s) runs the rollout + costate recursion of instance l (three trajectories per instance for
+//     the fused F(U,x+dx*h,t+h) / F(U,x,t) / F(U+h*dUdt,x+dx*h,t+h) evaluation) straight out of the instances'
+//     shared-memory blocks; the per-instance block stride is odd in 8-byte words so those lane-per-instance
+//     accesses are bank-conflict free.  The stage-parallel part of F (dHdu, cgmres.hpp:156-161) is taken off
+//     that serial path and evaluated by the owning warp, one stage per lane.
 //
 // Arithmetic: FMA contraction on (this header is compiled without -fmad=false), tree-ordered reductions.
 // Same algorithm, different rounding: judged to the north-star tolerances (1e-9 per update, 1e-6 closed loop),
-// not bit for bit.  EXACT_SUMS=true (debug / verification build of the same kernel inside the -fmad=false
-// translation unit) replaces the shuffle reductions by the reference's sequential sums, done lane-per-instance
-// by the first warp, and is bit-identical to the reference.
+// not bit for bit.  EXACT_SUMS=true (verification build of the same kernel inside the -fmad=false translation
+// unit) replaces the shuffle reductions by the reference's sequential sums, done lane-per-instance by the first
+// warp, and is bit-identical to the reference.
 #pragma once
 #include <float.h>
 #include <stdint.h>
@@ -30,12 +35,9 @@
 namespace cgmres_b200 {
 namespace fast {
 
-constexpr int kSmemBudget = 227 * 1024 - 2048;  // leave the per-CTA reserved shared memory of up to 2 CTAs
+constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved kilobyte
 #ifndef CG_FAST_GCAP
-#define CG_FAST_GCAP 12  // max instances (= warps) per CTA
-#endif
-#ifndef CG_FAST_WARPS
-#define CG_FAST_WARPS 16  // max resident warps (= instances) per SM: 16 warps leave 128 registers per thread
+#define CG_FAST_GCAP 16  // max instances (= warps) per CTA: 16 warps leave 128 registers per thread
 #endif
 
 template <class M>
@@ -44,28 +46,24 @@ struct Lay {
   static constexpr int L = nu * dv;
   static constexpr int np1 = np > 0 ? np : 1;
   static constexpr int XT = nx * (dv > 1 ? dv - 1 : 1);  // stored rollout states xtau[1..dv-1]
+  static constexpr int LTN = nx * dv;                    // stored costates ltau[1..dv]
   static constexpr int Q = (L + 31) / 32;                // vector elements per lane
-  // per-instance shared-memory block, offsets in doubles
-  // (U itself is not kept on chip: it is re-read from global memory -- an L2 hit, the CTA touched it a few
-  //  microseconds earlier -- where U + h*v is formed and in the final update.)
-  static constexpr int oF1 = 0;           // U during the first evaluation, then F(U, x+dx*h, t+h) (cgmres.hpp:202)
-  static constexpr int oX = oF1 + L;      // U + h*v  ->  w         (cgmres.hpp:168-174), products in EXACT_SUMS
-  static constexpr int oV = oX + L;       // km basis columns r_0..r_{km-1}, un-normalised (gmres.hpp:11)
-  static constexpr int oXT = oV + km * L; // rollout states xtau[1..dv-1] of the Arnoldi sweeps / trajectory A
-  // The fused first evaluation runs three trajectories; B and C park their rollout states in basis columns
-  // km-1 and 0 (both unused until r0 exists) when a plane fits in a column, else in two extra planes.
-  static constexpr bool xt_alias = (XT <= L) && (km >= 5);
-  static constexpr int oXTB = xt_alias ? oV + (km - 1) * L : oXT + XT;
-  static constexpr int oXTC = xt_alias ? oV : oXT + 2 * XT;
-  static constexpr int oLT = oXT + (xt_alias ? 1 : 3) * XT;  // costates ltau[1..dv] of the Arnoldi sweeps
-  static constexpr int oS = oLT + nx * dv;                   // scalars
+  // per-instance shared-memory block, offsets in doubles.  (U itself is not kept on chip: it is re-read from
+  // global memory -- an L2 hit, the CTA touched it microseconds earlier -- where U + h*v is formed and in the
+  // final update.)
+  static constexpr int oF1 = 0;        // first evaluation: U -> F(U,x+dx*h,t+h) in place; then F_dxh_h (cgmres.hpp:202)
+  static constexpr int oB = oF1 + L;   // first evaluation: U -> F(U,x,t) in place; afterwards the costate plane
+  static constexpr int oX = oB + L;    // first evaluation: U+h*dUdt -> F(..) in place; then U+h*v -> w (cgmres.hpp:168-174)
+  static constexpr int oXT = oX + L;   // rollout states of trajectory A / of the Arnoldi sweeps
+  static constexpr int oXTB = oXT + XT;   // rollout states of trajectory B (first evaluation only)
+  static constexpr int oXTC = oXTB + XT;  // rollout states of trajectory C (first evaluation only)
+  static constexpr bool lt_alias = LTN <= L;  // costates of the Arnoldi sweeps reuse the dead F(U,x,t) area
+  static constexpr int oLT = lt_alias ? oB : oXTC + XT;
+  static constexpr int oS = oXTC + XT + (lt_alias ? 0 : LTN);  // scalars
   // scalar slots
   static constexpr int sR = 0;                         // packed upper triangle R(i,j), i<=j<km
   static constexpr int sG = sR + km * (km + 1) / 2;    // 3*km reflectors
-  static constexpr int sRHO = sG + 3 * km;             // km+1
-  static constexpr int sVS = sRHO + km + 1;            // km+1 basis scales 1/||r_k||
-  static constexpr int sHC = sVS + km + 1;             // km+2 current Hessenberg column
-  static constexpr int sX = sHC + km + 2;              // x
+  static constexpr int sX = sG + 3 * km;               // x
   static constexpr int sXH = sX + nx;                  // x + dxdt*h
   static constexpr int sP = sXH + nx;                  // p(t) (repeat mode) / first stage
   static constexpr int sRED = sP + np1;                // reduction result slot (EXACT_SUMS)
@@ -74,18 +72,150 @@ struct Lay {
   static constexpr int raw = oS + sCount;
   // odd number of 8-byte words per instance => lane-per-instance accesses hit distinct banks
   static constexpr int stride = (raw % 2 == 0) ? raw + 1 : raw;
-  static constexpr int G_fit = kSmemBudget / (stride * 8);
-  // instances per CTA (one warp each): what fits in shared memory, capped at 12 warps so that every thread
-  // can keep ~168 registers (the register file, not shared memory, bounds the small-L models)
-  static constexpr int G = G_fit > CG_FAST_GCAP ? CG_FAST_GCAP : G_fit;
-  // co-resident CTAs (they run out of phase, which overlaps one CTA's serial sweep with another's vector work):
-  // bounded by shared memory (G_fit instances per SM) and by CG_FAST_WARPS warps per SM (register budget)
-  static constexpr int inst_per_sm = G_fit > CG_FAST_WARPS ? CG_FAST_WARPS : G_fit;
-  static constexpr int ctas_per_sm = (inst_per_sm / G) < 1 ? 1 : (inst_per_sm / G);
+  // tensor memory: 2*Q 32-bit columns per basis vector per instance; warps w, w+4, w+8, ... share a lane quarter
+  static constexpr int tcols_vec = 2 * Q;
+  static constexpr int tcols_inst = km * tcols_vec;
+  static constexpr int G_tmem = 4 * (512 / tcols_inst);
+  static constexpr int G_smem = (kSmemBudget - 64) / (stride * 8);
+  static constexpr int G_fit = G_smem < G_tmem ? G_smem : G_tmem;
+  static constexpr int G = G_fit > CG_FAST_GCAP ? CG_FAST_GCAP : G_fit;  // instances per CTA, one CTA per SM
   static constexpr int threads = 32 * G;
-  static constexpr size_t smem_bytes = (size_t)G * stride * 8;
+  static constexpr size_t smem_bytes = (size_t)G * stride * 8 + 64;  // + TMEM base address word
+  // TMEM columns this CTA allocates: a power of two >= 32 covering ceil(G/4) column slots
+  static constexpr int tcols_need = ((G + 3) / 4) * tcols_inst;
+  static constexpr int tcols_alloc = tcols_need <= 32 ? 32 : tcols_need <= 64 ? 64 : tcols_need <= 128 ? 128
+                                   : tcols_need <= 256 ? 256 : 512;
+  static_assert(tcols_need <= 512, "Krylov basis does not fit in tensor memory");
   static __host__ __device__ constexpr int r(int i, int j) { return sR + j * (j + 1) / 2 + i; }
 };
+
+// ---- tensor memory as per-lane private storage -----------------------------------------------------------------
+// tcgen05.{st,ld}.32x32b.xN: thread i of the warp moves N consecutive 32-bit columns of TMEM lane (base + i).
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r);
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_st<1>(uint32_t t, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t), "r"(r[0]) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<2>(uint32_t t, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t), "r"(r[0]), "r"(r[1]) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<4>(uint32_t t, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<8>(uint32_t t, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<16>(uint32_t t, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};" ::"r"(t),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<1>(uint32_t t, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(t) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<2>(uint32_t t, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(t) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t t, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(t)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t t, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(t)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t t, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(t)
+      : "memory");
+}
+
+// move NW 32-bit words (any NW <= 31) as power-of-two chunks
+template <int NW, int OFF = 0>
+__device__ __forceinline__ void tmem_st_words(uint32_t taddr, const uint32_t* r) {
+  if constexpr (NW >= 16) {
+    tmem_st<16>(taddr + OFF, r + OFF);
+    tmem_st_words<NW - 16, OFF + 16>(taddr, r);
+  } else if constexpr (NW >= 8) {
+    tmem_st<8>(taddr + OFF, r + OFF);
+    tmem_st_words<NW - 8, OFF + 8>(taddr, r);
+  } else if constexpr (NW >= 4) {
+    tmem_st<4>(taddr + OFF, r + OFF);
+    tmem_st_words<NW - 4, OFF + 4>(taddr, r);
+  } else if constexpr (NW >= 2) {
+    tmem_st<2>(taddr + OFF, r + OFF);
+    tmem_st_words<NW - 2, OFF + 2>(taddr, r);
+  } else if constexpr (NW == 1) {
+    tmem_st<1>(taddr + OFF, r + OFF);
+  }
+}
+template <int NW, int OFF = 0>
+__device__ __forceinline__ void tmem_ld_words(uint32_t taddr, uint32_t* r) {
+  if constexpr (NW >= 16) {
+    tmem_ld<16>(taddr + OFF, r + OFF);
+    tmem_ld_words<NW - 16, OFF + 16>(taddr, r);
+  } else if constexpr (NW >= 8) {
+    tmem_ld<8>(taddr + OFF, r + OFF);
+    tmem_ld_words<NW - 8, OFF + 8>(taddr, r);
+  } else if constexpr (NW >= 4) {
+    tmem_ld<4>(taddr + OFF, r + OFF);
+    tmem_ld_words<NW - 4, OFF + 4>(taddr, r);
+  } else if constexpr (NW >= 2) {
+    tmem_ld<2>(taddr + OFF, r + OFF);
+    tmem_ld_words<NW - 2, OFF + 2>(taddr, r);
+  } else if constexpr (NW == 1) {
+    tmem_ld<1>(taddr + OFF, r + OFF);
+  }
+}
+// store / load this lane's Q-double slice of one basis vector (whole warp must call, converged)
+template <int Q>
+__device__ __forceinline__ void basis_store(uint32_t taddr, const double* v) {
+  uint32_t r[2 * Q];
+  __syncwarp();  // .sync.aligned: the whole warp must arrive converged
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    r[2 * q] = (uint32_t)__double2loint(v[q]);
+    r[2 * q + 1] = (uint32_t)__double2hiint(v[q]);
+  }
+  tmem_st_words<2 * Q>(taddr, r);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+template <int Q>
+__device__ __forceinline__ void basis_load(uint32_t taddr, double* v) {
+  uint32_t r[2 * Q];
+  __syncwarp();
+  tmem_ld_words<2 * Q>(taddr, r);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < Q; q++) v[q] = __hiloint2double((int)r[2 * q + 1], (int)r[2 * q]);
+}
 
 // Forward Euler rollout of one instance by ONE lane (cgmres.hpp:132-140): returns xtau[dv] in xc, stores
 // xtau[1..dv-1] to the scratch plane xt.
@@ -192,9 +322,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// The kernel.  grid = ceil(n / G) CTAs of 32*G threads; dynamic shared memory = Lay<M>::smem_bytes.
+// The kernel.  grid = ceil(n / G) CTAs of 32*G threads, one CTA per SM;
+// dynamic shared memory = Lay<M>::smem_bytes.
 template <class M, class Sim, bool PFULL, bool EXACT_SUMS>
-__global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_kernel(const FastArgs a) {
+__global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastArgs a) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, L = Y::L, km = Y::km, Q = Y::Q, G = Y::G;
   constexpr double hh = M::h;
@@ -204,14 +335,24 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t n0 = (int64_t)blockIdx.x * G;
   const int n_here = (int)((a.n - n0) < (int64_t)G ? (a.n - n0) : (int64_t)G);
-  const bool has = wid < n_here;            // this warp owns a live instance
-  const int64_t n = n0 + wid;               // its global index
+  const bool has = wid < n_here;  // this warp owns a live instance (warp-uniform)
+  const int64_t n = n0 + wid;     // its global index
   double* const blk = sm + (size_t)wid * Y::stride;
   double* const sc = blk + Y::oS;
-  auto col = [&](int k) { return blk + Y::oV + k * L; };
   auto inst_blk = [&](int g) { return sm + (size_t)g * Y::stride; };
 
-  // ---- phase 0: state in.  U -> F1 area, X = U + h*dUdt (input of the third trajectory), x, p(t) ----------
+  // ---- tensor memory: one allocation of all 512 columns, released at the end by the same warp ----------------
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)G * Y::stride);
+  if (wid == 0) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tmem_slot);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst),
+                 "r"((uint32_t)Y::tcols_alloc)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+
+  // ---- phase 0: state in.  F1 and B areas <- U, X <- U + h*dUdt (third trajectory), x, p(t) -----------------
   if (has) {
     const double* Ug = a.U + n * (int64_t)L;
     const double* dUg = a.dUdt + n * (int64_t)L;
@@ -220,7 +361,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
       const int j = lane + 32 * q;
       if (j < L) {
         const double uu = Ug[j];
-        blk[Y::oF1 + j] = uu;  // the F1 area holds U until F1 exists
+        blk[Y::oF1 + j] = uu;
+        blk[Y::oB + j] = uu;
         double v = dUg[j] * hh;  // cgmres.hpp:168-169
         blk[Y::oX + j] = v + uu;
       }
@@ -230,6 +372,11 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     if (lane == 0) sc[Y::sFLAG] = 0.0;
   }
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // this warp's lane quarter (warp id % 4) and column slot (warp id / 4) of the allocation
+  const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (wid & 3)) << 16) + (uint32_t)((wid >> 2) * Y::tcols_inst);
+  auto tcol = [&](int k) { return tbase + (uint32_t)(k * Y::tcols_vec); };
+
   if (has && lane == 0) {  // x + dxdt*h, cgmres.hpp:83-85
     double x[nx], u0[nu], p0[Y::np1], f[nx];
 #pragma unroll
@@ -247,43 +394,44 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   }
   __syncthreads();
 
-  // ---- phase 1: the three Krylov-independent F evaluations, one lane per (instance, trajectory) -----------
-  //   A: F(U, x+dx*h, t+h) -> col 1     B: F(U, x, t) -> col 2     C: F(U+h*dUdt, x+dx*h, t+h) -> col 3
+  // ---- phase 1: the three Krylov-independent F evaluations, one lane per (instance, trajectory), in place ---
+  //   A: F(U, x+dx*h, t+h) in the F1 area   B: F(U, x, t) in the B area   C: F(U+h*dUdt, x+dx*h, t+h) in X
   if (threadIdx.x < 3 * n_here) {
     const int g = threadIdx.x / 3, tr = threadIdx.x % 3;
     double* b = inst_blk(g);
     const double* s = b + Y::oS;
     const double* pf = PFULL ? a.ptau + (n0 + g) * (int64_t)((M::dv + 1) * np) : nullptr;
+    double* io = b + (tr == 0 ? Y::oF1 : (tr == 1 ? Y::oB : Y::oX));
     double* plane = b + (tr == 0 ? Y::oXT : (tr == 1 ? Y::oXTB : Y::oXTC));
-    lane_sweep_full<M>(tr == 2 ? b + Y::oX : b + Y::oF1, b + Y::oV + (1 + tr) * L, plane,
-                       tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? a.dtau_t : a.dtau_th, s + Y::sP, pf);
+    lane_sweep_full<M>(io, io, plane, tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? a.dtau_t : a.dtau_th, s + Y::sP,
+                       pf);
   }
   __syncthreads();
 
-  // ---- phase 2: F1, b, r0 = b - A*dUdt; rho0 ---------------------------------------------------------------
+  // ---- phase 2: b, r0 = b - A*dUdt (F1 stays where trajectory A left it); rho0 -------------------------------
   double w[Q];  // working vector slice (r0, then each new Krylov vector)
   double ssq = 0.0;
+#pragma unroll
+  for (int q = 0; q < Q; q++) w[q] = 0.0;
   if (has) {
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       const int j = lane + 32 * q;
-      w[q] = 0.0;
       if (j < L) {
-        const double fa = col(1)[j], fb = col(2)[j], fc = col(3)[j];
-        blk[Y::oF1 + j] = fa;
+        const double fa = blk[Y::oF1 + j], fb = blk[Y::oB + j], fc = blk[Y::oX + j];
         double b = fb * c1;  // cgmres.hpp:94-96
         b = b - fa;
         b = b * inv_h;
         double ax = fc - fa;  // cgmres.hpp:173-174
         ax = ax * inv_h;
         w[q] = b - ax;  // gmres.hpp:34
-        col(0)[j] = w[q];
         if (EXACT_SUMS)
           blk[Y::oX + j] = w[q] * w[q];
         else
           ssq += w[q] * w[q];
       }
     }
+    basis_store<Q>(tcol(0), w);  // r_0, un-normalised
   }
   // reductions: FAST = butterfly inside the owning warp; EXACT = lane-per-instance sequential sums by warp 0
   auto reduce = [&](double partial) -> double {
@@ -324,7 +472,6 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   // ---- Arnoldi iterations ------------------------------------------------------------------------------------
   // R (packed triangle) and the reflectors are warp-uniform and touched a few times per iteration only: they
   // live in this instance's shared-memory scalars (written by lane 0, read by all lanes after __syncwarp).
-
 #pragma unroll
   for (int k = 0; k < km; k++) {
     // X = U + h*v_k, v_k = r_k*s_k (cgmres.hpp:168-169); w currently holds r_k
@@ -340,7 +487,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
       }
     }
     __syncthreads();
-    if (threadIdx.x < n_here) {  // transposed sweep: lane = instance; w = A v_k lands in X (gmres.hpp:48)
+    if (threadIdx.x < n_here) {  // transposed recursions: lane = instance (cgmres.hpp:132-153)
       double* b = inst_blk(threadIdx.x);
       const double* s = b + Y::oS;
       if (s[Y::sFLAG] == 0.0) {
@@ -351,7 +498,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     __syncthreads();
     if (solving) {
       // stage-parallel dHdu (cgmres.hpp:156-161) and (F - F1)*inv_h (cgmres.hpp:173-174), one stage per lane;
-      // w_i overwrites u_i in X (same lane reads before it writes)
+      // w_i overwrites u_i in X (same lane reads before it writes): w = A v_k (gmres.hpp:48)
       const double* pf = PFULL ? a.ptau + n * (int64_t)((M::dv + 1) * np) : nullptr;
       for (int i = lane; i < M::dv; i += 32) {
         double xi[nx], u[nu], p[Y::np1], lm[nx], hu[nu];
@@ -378,23 +525,25 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         w[q] = (j < L) ? blk[Y::oX + j] : 0.0;
       }
     }
-    // modified Gram-Schmidt (gmres.hpp:52-58) against r_i*s_i, i = 0..k
+    // modified Gram-Schmidt (gmres.hpp:52-58) against v_i = r_i*s_i, i = 0..k; each r_i slice comes from TMEM once
     double hc[km + 2];
 #pragma unroll
     for (int i = 0; i < km + 2; i++) hc[i] = 0.0;
 #pragma unroll
     for (int i = 0; i <= k; i++) {
+      double c[Q];
       double part = 0.0;
       if (solving) {
+        basis_load<Q>(tcol(i), c);
 #pragma unroll
         for (int q = 0; q < Q; q++) {
           const int j = lane + 32 * q;
+          c[q] = c[q] * vs[i];
           if (j < L) {
-            const double v = col(i)[j] * vs[i];
             if (EXACT_SUMS)
-              blk[Y::oX + j] = v * w[q];
+              blk[Y::oX + j] = c[q] * w[q];
             else
-              part += v * w[q];
+              part += c[q] * w[q];
           }
         }
       }
@@ -403,12 +552,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
       if (solving) {
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-          const int j = lane + 32 * q;
-          if (j < L) {
-            const double v = col(i)[j] * vs[i];
-            const double t = v * hik;
-            w[q] = w[q] - t;
-          }
+          const double t = c[q] * hik;
+          w[q] = w[q] - t;
         }
       }
     }
@@ -436,13 +581,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     if (solving) {
       vs[k + 1] = 1.0 / hn;  // gmres.hpp:67
       hc[k + 1] = hn;
-      if (k + 1 < km) {  // the last vector only contributes its Hessenberg column
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-          const int j = lane + 32 * q;
-          if (j < L) col(k + 1)[j] = w[q];
-        }
-      }
+      if (k + 1 < km) basis_store<Q>(tcol(k + 1), w);  // the last vector only contributes its Hessenberg column
       // stored reflectors on the new column (gmres.hpp:71-77), new reflector (78-85), residual (88-90)
 #pragma unroll
       for (int i = 0; i < k; i++) {
@@ -500,21 +639,30 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   if (has) {
     double* Ug = a.U + n * (int64_t)L;
     double* dUg = a.dUdt + n * (int64_t)L;
+    double s[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) s[q] = 0.0;
+    if (apply) {  // s = sum_c v_c*y_c in column order (matrix.hpp:82-91)
+#pragma unroll
+      for (int c = 0; c < km; c++) {
+        if (c < ncol) {
+          double cv[Q];
+          basis_load<Q>(tcol(c), cv);
+#pragma unroll
+          for (int q = 0; q < Q; q++) {
+            const double v = cv[q] * vs[c];
+            s[q] += v * rho[c];
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       const int j = lane + 32 * q;
       if (j < L) {
         double d = dUg[j];  // second (L2-resident) read instead of 2*Q live registers through the whole solve
         if (apply) {
-          double s = 0.0;
-#pragma unroll
-          for (int c = 0; c < km; c++) {
-            if (c < ncol) {
-              const double v = col(c)[j] * vs[c];
-              s += v * rho[c];
-            }
-          }
-          d = d + s;
+          d = d + s[q];
           dUg[j] = d;
         }
         const double inc = d * M::dt;
@@ -544,6 +692,16 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
       }
       a.status[n] = code | (ncol << 8);
     }
+  }
+
+  // ---- release tensor memory ------------------------------------------------------------------------------------
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (wid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot),
+                 "r"((uint32_t)Y::tcols_alloc)
+                 : "memory");
   }
 }
 
