@@ -2,6 +2,11 @@
 // reductions (default nvcc floating-point flags; NOT -fmad=false).
 #include "fast_update.cuh"
 
+// experiment knob (tools/sweep_build.sh): build the "fast" entry point with the reference's sequential sums
+#ifndef CG_FAST_SEQ_SUMS
+#define CG_FAST_SEQ_SUMS false
+#endif
+
 namespace cgmres_b200 {
 namespace {
 template <class M, class Sim>
@@ -11,15 +16,15 @@ cudaError_t launch_t(bool pfull, const FastArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((a.n + Y::G - 1) / Y::G);
   cudaError_t e;
   if (pfull) {
-    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, true, CG_FAST_SEQ_SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Y::smem_bytes);
     if (e != cudaSuccess) return e;
-    fast::control_kernel<M, Sim, true, false><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
+    fast::control_kernel<M, Sim, true, CG_FAST_SEQ_SUMS><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
   } else {
-    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, false, CG_FAST_SEQ_SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Y::smem_bytes);
     if (e != cudaSuccess) return e;
-    fast::control_kernel<M, Sim, false, false><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
+    fast::control_kernel<M, Sim, false, CG_FAST_SEQ_SUMS><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
   }
   return cudaGetLastError();
 }

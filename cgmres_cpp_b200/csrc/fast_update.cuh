@@ -36,8 +36,11 @@ namespace cgmres_b200 {
 namespace fast {
 
 constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved kilobyte
+// max instances (= warps) per CTA.  Register file: 16 warps leave 128 registers per thread, 20 warps 102; the
+// kernels with long vector slices (Q >= 8 per lane) or a 4-state sweep need ~110-125, semiactive ~95 (GPU sweep in
+// profiles/README.md: msd 16 > 18/20 (spills) > 12; semiactive 20 > 16).
 #ifndef CG_FAST_GCAP
-#define CG_FAST_GCAP 16  // max instances (= warps) per CTA: 16 warps leave 128 registers per thread
+#define CG_FAST_GCAP(Q, NX) (((Q) >= 8 || (NX) > 2) ? 16 : 20)
 #endif
 
 template <class M>
@@ -78,7 +81,7 @@ struct Lay {
   static constexpr int G_tmem = 4 * (512 / tcols_inst);
   static constexpr int G_smem = (kSmemBudget - 64) / (stride * 8);
   static constexpr int G_fit = G_smem < G_tmem ? G_smem : G_tmem;
-  static constexpr int G = G_fit > CG_FAST_GCAP ? CG_FAST_GCAP : G_fit;  // instances per CTA, one CTA per SM
+  static constexpr int G = G_fit > CG_FAST_GCAP(Q, nx) ? CG_FAST_GCAP(Q, nx) : G_fit;  // instances per CTA, one CTA per SM
   static constexpr int threads = 32 * G;
   static constexpr size_t smem_bytes = (size_t)G * stride * 8 + 64;  // + TMEM base address word
   // TMEM columns this CTA allocates: a power of two >= 32 covering ceil(G/4) column slots
