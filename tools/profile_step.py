@@ -10,14 +10,14 @@ from oracle import pyoracle as po  # noqa: E402  (seeded synthetic inputs only)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="msd", choices=("msd", "arm", "semiactive"))
-ap.add_argument("--mode", default="exact", choices=("exact", "fast"))
+ap.add_argument("--mode", default="fast", choices=("exact", "fast", "onchip_exact"))
 ap.add_argument("--instances", type=int, default=0)
 ap.add_argument("--steps", type=int, default=6)
 a = ap.parse_args()
 mid = {"msd": 0, "arm": 1, "semiactive": 2}[a.model]
 n = a.instances or {"msd": 65536, "arm": 262144, "semiactive": 131072}[a.model]
 x0, p, u0 = po.synthetic_batch(mid, n)
-c = cg.BatchedCgmres(mid, n, mode=cg.MODE_FAST if a.mode == "fast" else cg.MODE_EXACT)
+c = cg.BatchedCgmres(mid, n, mode={"exact": cg.MODE_EXACT, "fast": cg.MODE_FAST, "onchip_exact": cg.MODE_ONCHIP_EXACT}[a.mode])
 c.set_ptau_repeat(p)
 c.init_u0(u0)
 c.init_u0_newton(u0, x0, p, 10)

@@ -3,7 +3,7 @@
 flags="$1"
 touch cgmres_cpp_b200/csrc/fast_kernels.cu
 make -C cgmres_cpp_b200/csrc FAST_EXTRA="$flags" > /dev/null 2>&1 || { echo "build failed: $flags"; exit 1; }
-python bench.py --steps 40 --warmup 4 --no-cpu-baseline --mode fast 2>&1 | tail -1 > /tmp/sweep_line.json
+python bench.py --steps 40 --warmup 4 --no-cpu-baseline --no-other-modes --mode fast 2>&1 | tail -1 > /tmp/sweep_line.json
 python tools/drift_full.py --model msd > /tmp/drift.json
 python - "$flags" <<'PY'
 import json, sys
