@@ -39,6 +39,12 @@ constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved ki
 // max instances (= warps) per CTA.  Register file: 16 warps leave 128 registers per thread, 20 warps 102; the
 // kernels with long vector slices (Q >= 8 per lane) or a 4-state sweep need ~110-125, semiactive ~95 (GPU sweep in
 // profiles/README.md: msd 16 > 18/20 (spills) > 12; semiactive 20 > 16).
+#ifndef CG_FAST_MAXCTAS
+#define CG_FAST_MAXCTAS 1
+#endif
+#ifdef CG_FAST_GFORCE  // tuning override: same cap for every model
+#define CG_FAST_GCAP(Q, NX) (CG_FAST_GFORCE)
+#endif
 #ifndef CG_FAST_GCAP
 #define CG_FAST_GCAP(Q, NX) (((Q) >= 8 || (NX) > 2) ? 16 : 20)
 #endif
@@ -82,6 +88,9 @@ struct Lay {
   static constexpr int G_smem = (kSmemBudget - 64) / (stride * 8);
   static constexpr int G_fit = G_smem < G_tmem ? G_smem : G_tmem;
   static constexpr int G = G_fit > CG_FAST_GCAP(Q, nx) ? CG_FAST_GCAP(Q, nx) : G_fit;  // instances per CTA, one CTA per SM
+  // CTAs that can be co-resident on one SM (shared memory, tensor-memory columns, 16-warp register budget)
+  static constexpr int ctas_per_sm_ = (G_fit / G) < 1 ? 1 : (G_fit / G);
+  static constexpr int ctas_per_sm = ctas_per_sm_ > CG_FAST_MAXCTAS ? CG_FAST_MAXCTAS : ctas_per_sm_;
   static constexpr int threads = 32 * G;
   static constexpr size_t smem_bytes = (size_t)G * stride * 8 + 64;  // + TMEM base address word
   // TMEM columns this CTA allocates: a power of two >= 32 covering ceil(G/4) column slots
@@ -328,7 +337,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // The kernel.  grid = ceil(n / G) CTAs of 32*G threads, one CTA per SM;
 // dynamic shared memory = Lay<M>::smem_bytes.
 template <class M, class Sim, bool PFULL, bool EXACT_SUMS>
-__global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastArgs a) {
+__global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_kernel(const FastArgs a) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, L = Y::L, km = Y::km, Q = Y::Q, G = Y::G;
   constexpr double hh = M::h;
