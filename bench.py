@@ -109,33 +109,6 @@ def visible_gpu_index(local_rank: int) -> int:
 
 
 # ----------------------------------------------------------------------------------------------
-def plant_step_host(model: str, x: np.ndarray, u: np.ndarray) -> None:
-    """Host-side plant of the e2e loop (in the reference the plant is main.cpp's job, not the controller's):
-    x += Simulator::dxdt(x,u)*dt, vectorised over the batch.  Same formulas as <example>/simulator.hpp."""
-    dt = 0.001
-    if model == "msd":
-        f2 = -x[:, 0] + x[:, 1] - 2.0 * x[:, 2] + x[:, 3] + u[:, 0]
-        f3 = x[:, 0] - x[:, 1] + x[:, 2] - x[:, 3] + u[:, 1]
-        x[:, 0] += x[:, 2] * dt
-        x[:, 1] += x[:, 3] * dt
-        x[:, 2] += f2 * dt
-        x[:, 3] += f3 * dt
-    elif model == "arm":
-        d = x[:, 0] - x[:, 1]
-        sd, cd, s1 = np.sin(d), np.cos(d), np.sin(x[:, 1])
-        f2 = -6.25 * x[:, 2] + 15.6 * u[:, 0]
-        f3 = (0.905016 * x[:, 2] * x[:, 2] * sd + 39.1111 * s1 - 14.1183 * cd * u[:, 0] + 5.65635 * cd * x[:, 2]
-              + 0.0407448 * (x[:, 2] - x[:, 3]))
-        x[:, 0] += x[:, 2] * dt
-        x[:, 1] += x[:, 3] * dt
-        x[:, 2] += f2 * dt
-        x[:, 3] += f3 * dt
-    else:
-        f1 = -x[:, 0] - u[:, 0] * x[:, 1]
-        x[:, 0] += x[:, 1] * dt
-        x[:, 1] += f1 * dt
-
-
 def cpu_baseline_run(model_id: int, n_inst: int, steps: int, threads: int, seed: int = 12345):
     """The reference's CPU path on `threads` host threads over the first n_inst instances of the GPU workload."""
     from oracle import pyoracle as po
@@ -254,14 +227,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     uh = torch.empty((n, ctl.dim_u), dtype=torch.float64).pin_memory()
     xh.copy_(torch.from_numpy(x_end))
     xn, un = xh.numpy(), uh.numpy()
+    # the e2e loop is the reference's main(): u = control(x) through HOST buffers, then the plant step on the host
+    # (cgmres_b200_plant_step_host = the Simulator functor of include/<example>/simulator.hpp, compiled host code)
     for _ in range(3):
         ctl.control_raw(uh.data_ptr(), xh.data_ptr())
-        plant_step_host(model, xn, un)
+        cg.plant_step_host(model_id, xn, un)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ctl.control_raw(uh.data_ptr(), xh.data_ptr())  # H2D x, update kernel, D2H u, synchronises
-        plant_step_host(model, xn, un)
+        cg.plant_step_host(model_id, xn, un)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -343,7 +318,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             },
             "e2e": {"value": n * world * e2e_steps / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": n * ctl.dim_x * 8, "d2h_bytes_per_step": n * ctl.dim_u * 8,
-                    "steps": e2e_steps, "api": "cgmres_b200_control(u_host, x_host) + host plant step"},
+                    "steps": e2e_steps, "api": "cgmres_b200_control(u_host, x_host) + cgmres_b200_plant_step_host (the loop of the reference main.cpp)"},
             "gpu_launches": int(launches),
             "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w_max")},
             "finite": bool(ok.item() > 0.5), "exit_hist_last_step": exit_hist,

@@ -189,6 +189,12 @@ class BatchedCgmres:
         return s & 0xFF, s >> 8
 
 
+def plant_step_host(model: int, x: np.ndarray, u: np.ndarray) -> None:
+    """x[n][dim_x] += Simulator::dxdt(x,u)*dt in place on the host (the plant step of the reference's main loop)."""
+    assert x.dtype == np.float64 and u.dtype == np.float64 and x.flags.c_contiguous and u.flags.c_contiguous
+    check(lib().cgmres_b200_plant_step_host(model, x.shape[0], C.c_void_p(x.ctypes.data), C.c_void_p(u.ctypes.data)))
+
+
 def launch_count() -> int:
     return int(lib().cgmres_b200_launch_count())
 

@@ -226,6 +226,17 @@ struct cgmres_b200_controller {
   if (!(h)) return fail(CGMRES_B200_EINVAL, "null handle")
 #define ON_DEVICE(h) CU(cudaSetDevice((h)->device))
 
+template <class Sim>
+static void plant_host(int64_t n, double* x, const double* u) {
+  constexpr int nx = Sim::dim_x, nu = Sim::dim_u;
+  for (int64_t i = 0; i < n; i++) {
+    double d[nx];
+    Sim::dxdt(d, x + i * nx, u + i * nu);
+    for (int j = 0; j < nx; j++) d[j] = d[j] * Sim::dt;          // mul(dxdt, dxdt, dt)
+    for (int j = 0; j < nx; j++) x[i * nx + j] = x[i * nx + j] + d[j];  // add(x, x, dxdt)
+  }
+}
+
 extern "C" {
 
 const char* cgmres_b200_last_error(void) { return g_err.c_str(); }
@@ -435,6 +446,15 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
   if (!u || !x) return fail(CGMRES_B200_EINVAL, "null pointer");
   const size_t n = (size_t)h->n;
   const int nx = h->mi->dim_x, nu = h->mi->dim_u;
+  if (!h->soa()) {  // instance-major state == ABI layout: x straight into place, u straight out
+    if (n == 0) return 0;
+    CU(cudaMemcpyAsync(h->x, x, sizeof(double) * n * nx, cudaMemcpyHostToDevice, h->stream));
+    int rcu = h->launch_update(0);
+    if (rcu) return rcu;
+    CU(cudaMemcpyAsync(u, h->u_out, sizeof(double) * n * nu, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
   int rc = h->ensure_stage(n * (size_t)(nx + nu));
   if (rc) return rc;
   double* d_x = h->stage;
@@ -508,6 +528,16 @@ int cgmres_b200_get_status(cgmres_b200_handle h, int32_t* status) {
   CU(cudaMemcpyAsync(status, h->status, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+int cgmres_b200_plant_step_host(int model, int64_t n, double* x, const double* u) {
+  if (n < 0 || (n > 0 && (!x || !u))) return fail(CGMRES_B200_EINVAL, "bad plant_step_host arguments");
+  switch (model) {
+    case MODEL_MSD: plant_host<MassSpringDamperSimulator>(n, x, u); return 0;
+    case MODEL_ARM: plant_host<ArmPendulumSimulator>(n, x, u); return 0;
+    case MODEL_SEMIACTIVE: plant_host<SemiactiveDamperSimulator>(n, x, u); return 0;
+  }
+  return fail(CGMRES_B200_EINVAL, "unknown model");
 }
 
 int64_t cgmres_b200_launch_count(void) { return g_launches.load(); }

@@ -126,6 +126,12 @@ int cgmres_b200_set_state(cgmres_b200_handle h, const double* t, const double* U
 /* status[n] of the last update (see CGMRES_B200_EXIT_*) */
 int cgmres_b200_get_status(cgmres_b200_handle h, int32_t* status);
 
+/* Host-side plant of the reference's example loop, batched: x[n][dim_x] += Simulator::dxdt(x, u)*dt with
+ * u[n][dim_u] (<example>/main.cpp:74-76, <example>/simulator.hpp).  Plain host code on the caller's thread: the
+ * plant belongs to the user's program (in the reference it lives in main.cpp, not in the controller); this is the
+ * same Simulator functor the device epilogue inlines, for callers that drive control() from a non-C++ host. */
+int cgmres_b200_plant_step_host(int model, int64_t n, double* x, const double* u);
+
 /* kernels launched by this library in this process so far (for the benchmark's launch accounting) */
 int64_t cgmres_b200_launch_count(void);
 

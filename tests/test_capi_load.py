@@ -93,3 +93,24 @@ int main() {
                         "-lcgmres_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_host_plant_step_matches_reference_plant(built, oracle_port):
+    """cgmres_b200_plant_step_host is plain host code (the Simulator functor the kernels also inline): it must
+    reproduce the reference's x += Simulator::dxdt(x,u)*dt bit for bit (<example>/main.cpp:74-76)."""
+    import numpy as np
+
+    import cgmres_cpp_b200 as cg
+    from oracle import pyoracle as po
+
+    rng = np.random.default_rng(7)
+    for m in (cg.MSD, cg.SEMIACTIVE, cg.ARM):
+        d = cg.model_dims(m)
+        x = rng.normal(size=(50, d.dim_x))
+        u = rng.normal(size=(50, d.dim_u))
+        want = x.copy()
+        for i in range(50):
+            oracle_port.plant_step(m, want[i], u[i])
+        got = x.copy()
+        cg.plant_step_host(m, got, u)
+        assert np.array_equal(got, want), po.MODEL_NAMES[m]
