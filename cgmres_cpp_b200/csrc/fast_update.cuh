@@ -39,6 +39,11 @@ constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved ki
 // max instances (= warps) per CTA.  Register file: 16 warps leave 128 registers per thread, 20 warps 102; the
 // kernels with long vector slices (Q >= 8 per lane) or a 4-state sweep need ~110-125, semiactive ~95 (GPU sweep in
 // profiles/README.md: msd 16 > 18/20 (spills) > 12; semiactive 20 > 16).
+#ifndef CG_SWEEP_UNROLL
+#define CG_SWEEP_UNROLL 5  // stages per unrolled body of the serial recursions (exposes the next stages' loads)
+#endif
+#define CG_PRAGMA(x) _Pragma(#x)
+#define CG_UNROLL(n) CG_PRAGMA(unroll n)
 #ifndef CG_FAST_MAXCTAS
 #define CG_FAST_MAXCTAS 1
 #endif
@@ -239,7 +244,7 @@ __device__ __forceinline__ void lane_rollout(const double* in, double* xt, const
   double u[nu], p[Y::np1];
 #pragma unroll
   for (int j = 0; j < nx; j++) xc[j] = x0[j];
-#pragma unroll 2
+CG_UNROLL(CG_SWEEP_UNROLL)
   for (int i = 0; i < dv; i++) {
     double f[nx];
 #pragma unroll
@@ -271,7 +276,7 @@ __device__ __forceinline__ void lane_sweep_full(const double* in, double* out, d
 #pragma unroll
   for (int j = 0; j < np; j++) p[j] = pfull ? pfull[dv * np + j] : pconst[j];
   M::dPhidx(lmd, xc, p);  // cgmres.hpp:145
-#pragma unroll 2
+CG_UNROLL(CG_SWEEP_UNROLL)
   for (int i = dv - 1; i >= 0; i--) {  // cgmres.hpp:146-161
     double xi[nx], hu[nu], hx[nx];
 #pragma unroll
@@ -309,7 +314,7 @@ __device__ __forceinline__ void lane_sweep_costates(const double* in, double* xt
   M::dPhidx(lmd, xc, p);
 #pragma unroll
   for (int j = 0; j < nx; j++) lt[(dv - 1) * nx + j] = lmd[j];
-#pragma unroll 2
+CG_UNROLL(CG_SWEEP_UNROLL)
   for (int i = dv - 1; i > 0; i--) {
     double xi[nx], hx[nx];
 #pragma unroll
@@ -327,6 +332,10 @@ __device__ __forceinline__ void lane_sweep_costates(const double* in, double* xt
     }
   }
 }
+
+// 1.0/x, correctly rounded (identical to the IEEE division the reference performs), without the generic
+// division subroutine
+__device__ __forceinline__ double reciprocal(double x) { return __drcp_rn(x); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -353,7 +362,16 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   double* const sc = blk + Y::oS;
   auto inst_blk = [&](int g) { return sm + (size_t)g * Y::stride; };
 
-  // ---- tensor memory: one allocation of all 512 columns, released at the end by the same warp ----------------
+#ifdef CG_STAGGER_NS
+  // experiment: de-phase the co-resident CTAs of the first wave so one group's serial recursion overlaps the
+  // other group's vector work (they would otherwise start together and stay in lock step)
+  if (blockIdx.x >= gridDim.y * 0 + CG_STAGGER_FIRST && blockIdx.x < 2 * CG_STAGGER_FIRST) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)CG_STAGGER_NS * 2) {
+    }
+  }
+#endif
+  // ---- tensor memory: one allocation, released at the end by the same warp --------------------------------------
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)G * Y::stride);
   if (wid == 0) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tmem_slot);
@@ -443,7 +461,6 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
           ssq += w[q] * w[q];
       }
     }
-    basis_store<Q>(tcol(0), w);  // r_0, un-normalised
   }
   // reductions: FAST = butterfly inside the owning warp; EXACT = lane-per-instance sequential sums by warp 0
   auto reduce = [&](double partial) -> double {
@@ -452,7 +469,15 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     if (threadIdx.x < n_here) {
       double* b = inst_blk(threadIdx.x);
       double s = 0;
-      for (int j = 0; j < L; j++) s += b[Y::oX + j];
+      constexpr int BS = 10;  // loads of a batch are issued together; the adds keep the reference's order
+      for (int j0 = 0; j0 + BS <= L; j0 += BS) {
+        double v[BS];
+#pragma unroll
+        for (int q = 0; q < BS; q++) v[q] = b[Y::oX + j0 + q];
+#pragma unroll
+        for (int q = 0; q < BS; q++) s += v[q];
+      }
+      for (int j = (L / BS) * BS; j < L; j++) s += b[Y::oX + j];
       b[Y::oS + Y::sRED] = s;
     }
     __syncthreads();
@@ -461,12 +486,9 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
 
   int code = EXIT_FULL, ncol = 0;
   bool solving = has;
-  double rho[km + 1], vs[km + 1];
+  double rho[km + 1];
 #pragma unroll
-  for (int i = 0; i <= km; i++) {
-    rho[i] = 0.0;
-    vs[i] = 0.0;
-  }
+  for (int i = 0; i <= km; i++) rho[i] = 0.0;
   {
     const double rho0 = sqrt(reduce(ssq));  // gmres.hpp:37
     rho[0] = rho0;
@@ -475,7 +497,10 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         code = EXIT_RHO0;
         solving = false;
       } else {
-        vs[0] = 1.0 / rho0;  // gmres.hpp:44
+        const double inv = reciprocal(rho0);  // gmres.hpp:44: div() multiplies by the rounded reciprocal
+#pragma unroll
+        for (int q = 0; q < Q; q++) w[q] = w[q] * inv;
+        basis_store<Q>(tcol(0), w);  // v_0
       }
     }
   }
@@ -486,14 +511,13 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   // live in this instance's shared-memory scalars (written by lane 0, read by all lanes after __syncwarp).
 #pragma unroll
   for (int k = 0; k < km; k++) {
-    // X = U + h*v_k, v_k = r_k*s_k (cgmres.hpp:168-169); w currently holds r_k
+    // X = U + h*v_k (cgmres.hpp:168-169); w currently holds v_k
     if (solving) {
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int j = lane + 32 * q;
         if (j < L) {
-          double v = w[q] * vs[k];
-          v = v * hh;
+          const double v = w[q] * hh;
           blk[Y::oX + j] = v + a.U[n * (int64_t)L + j];
         }
       }
@@ -537,7 +561,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         w[q] = (j < L) ? blk[Y::oX + j] : 0.0;
       }
     }
-    // modified Gram-Schmidt (gmres.hpp:52-58) against v_i = r_i*s_i, i = 0..k; each r_i slice comes from TMEM once
+    // modified Gram-Schmidt (gmres.hpp:52-58) against v_i, i = 0..k; each v_i slice comes from TMEM once
     double hc[km + 2];
 #pragma unroll
     for (int i = 0; i < km + 2; i++) hc[i] = 0.0;
@@ -550,7 +574,6 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
 #pragma unroll
         for (int q = 0; q < Q; q++) {
           const int j = lane + 32 * q;
-          c[q] = c[q] * vs[i];
           if (j < L) {
             if (EXACT_SUMS)
               blk[Y::oX + j] = c[q] * w[q];
@@ -591,9 +614,13 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
       }
     }
     if (solving) {
-      vs[k + 1] = 1.0 / hn;  // gmres.hpp:67
       hc[k + 1] = hn;
-      if (k + 1 < km) basis_store<Q>(tcol(k + 1), w);  // the last vector only contributes its Hessenberg column
+      if (k + 1 < km) {  // the last vector only contributes its Hessenberg column
+        const double inv = reciprocal(hn);  // gmres.hpp:67
+#pragma unroll
+        for (int q = 0; q < Q; q++) w[q] = w[q] * inv;
+        basis_store<Q>(tcol(k + 1), w);  // v_{k+1}
+      }
       // stored reflectors on the new column (gmres.hpp:71-77), new reflector (78-85), residual (88-90)
 #pragma unroll
       for (int i = 0; i < k; i++) {
@@ -607,7 +634,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         const double sg = (ha < 0.0) ? -1.0 : 1.0;
         const double buf = -sg * sqrt((0.0 + ha * ha) + hb * hb);
         const double g0 = ha - buf, g1 = hb;
-        const double g2 = 2.0 / ((0.0 + g0 * g0) + g1 * g1);
+        const double g2 = 2.0 * reciprocal((0.0 + g0 * g0) + g1 * g1);  // == 2.0/x: scaling by 2 is exact
         if (lane == 0) {
           sc[Y::sG + 3 * k] = g0;
           sc[Y::sG + 3 * k + 1] = g1;
@@ -661,10 +688,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
           double cv[Q];
           basis_load<Q>(tcol(c), cv);
 #pragma unroll
-          for (int q = 0; q < Q; q++) {
-            const double v = cv[q] * vs[c];
-            s[q] += v * rho[c];
-          }
+          for (int q = 0; q < Q; q++) s[q] += cv[q] * rho[c];
         }
       }
     }

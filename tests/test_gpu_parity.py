@@ -305,3 +305,30 @@ def test_cpp_dropin_example_reproduces_reference_text_output(cg, oracle_best, tm
         for i in (0, 1, 57, steps - 1):
             ref_line = "%f" % (0.001 * i) + "".join("\t%f" % v for v in traj[i])
             assert lines[i] == ref_line, (name, i)
+
+
+def test_multiple_controller_heterogeneous_batch(cg, oracle_best):
+    """BASELINE config 5 / multiple_controller/main.cpp:89-118: a Model1 (mass_spring_damper) batch and a Model2
+    (arm_type_inverted_pendulum) batch advance side by side on one GPU, each handle on its own stream, interleaved
+    launch by launch.  Controllers never interact, so each batch must equal its stand-alone run (bit for bit) and
+    the oracle (msd bit for bit, arm to the bars)."""
+    n1, n2, steps = 96, 160, 300
+    x1, p1, u1 = po.synthetic_batch(po.MSD, n1, seed=11)
+    x2, p2, u2 = po.synthetic_batch(po.ARM, n2, seed=12)
+    c1, _ = make(cg, po.MSD, x1, p1, u1)
+    c2, _ = make(cg, po.ARM, x2, p2, u2)
+    for _ in range(steps):  # asynchronous launches on two independent streams
+        c1.step_closed_loop(1)
+        c2.step_closed_loop(1)
+    xa, xb = c1.get_x(), c2.get_x()
+    s1, _ = make(cg, po.MSD, x1, p1, u1)
+    s1.step_closed_loop(steps)
+    s2, _ = make(cg, po.ARM, x2, p2, u2)
+    s2.step_closed_loop(steps)
+    assert np.array_equal(xa, s1.get_x()) and np.array_equal(xb, s2.get_x())
+    w1 = oracle_best.run_closed_loop(po.MSD, x1, p1, u1, steps, n_threads=4)
+    w2 = oracle_best.run_closed_loop(po.ARM, x2, p2, u2, steps, n_threads=4)
+    assert np.array_equal(xa, w1["x_fin"])
+    assert np.abs(xb - w2["x_fin"]).max() <= TOL_X_ABS
+    for c in (c1, c2, s1, s2):
+        c.close()
