@@ -70,6 +70,11 @@ struct cgmres_b200_controller {
   int64_t n = 0, ld = 0;
   const ModelInfo* mi = nullptr;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // pipelined host-buffer control(): slices of the batch on side streams so that one slice's PCIe copies overlap
+  // another slice's kernel (instance-major modes only; instances are independent, so slicing changes nothing)
+  static constexpr int kSlices = 4;
+  cudaStream_t side[kSlices] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_begin = nullptr, ev_done[kSlices] = {nullptr, nullptr, nullptr, nullptr};
   double t = 0.0;          // cgmres.hpp:195 -- all instances of a handle step in lock step
   bool ptau_full = false;  // false: ptau holds one p per instance (set_ptau_repeat)
   double *x = nullptr, *U = nullptr, *dUdt = nullptr, *ptau = nullptr, *F1 = nullptr, *V = nullptr, *xtau = nullptr,
@@ -141,7 +146,44 @@ struct cgmres_b200_controller {
     cudaFree(u_out);
     cudaFree(status);
     cudaFree(stage);
+    for (int i = 0; i < kSlices; i++) {
+      if (side[i]) cudaStreamDestroy(side[i]);
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+    }
+    if (ev_begin) cudaEventDestroy(ev_begin);
     if (own_stream) cudaStreamDestroy(own_stream);
+  }
+
+  int ensure_side_streams() {
+    if (side[0]) return 0;
+    CU(cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming));
+    for (int i = 0; i < kSlices; i++) {
+      CU(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    }
+    return 0;
+  }
+
+  // on-chip modes: one update of instances [lo, lo+cnt) on stream s (pointer offsets into the instance-major state)
+  int launch_slice(int64_t lo, int64_t cnt, int plant, double dt_t, double dt_th, cudaStream_t s) {
+    FastArgs f;
+    const int64_t prow = ptau_full ? (int64_t)ptau_rows_full() : (int64_t)mi->dim_p;
+    f.n = cnt;
+    f.x = x + lo * mi->dim_x;
+    f.U = U + lo * L();
+    f.dUdt = dUdt + lo * L();
+    f.ptau = ptau + lo * prow;
+    f.u_out = u_out + lo * mi->dim_u;
+    f.status = status + lo;
+    f.dtau_t = dt_t;
+    f.dtau_th = dt_th;
+    f.plant = plant;
+    if (mode == CGMRES_B200_MODE_FAST)
+      CU(fast_launch_control(model, ptau_full, f, s));
+    else
+      CU(onchip_exact_launch_control(model, ptau_full, f, s));
+    g_launches++;
+    return 0;
   }
 
   double dtau(double tt) const { return mi->Tf * (1 - exp(-mi->alpha * tt)) / (double)mi->dv; }
@@ -149,22 +191,8 @@ struct cgmres_b200_controller {
   // one update for every instance; plant=1 also advances x (closed loop on device)
   int launch_update(int plant) {
     if (!soa()) {
-      FastArgs f;
-      f.n = n;
-      f.x = x;
-      f.U = U;
-      f.dUdt = dUdt;
-      f.ptau = ptau;
-      f.u_out = u_out;
-      f.status = status;
-      f.dtau_t = dtau(t);
-      f.dtau_th = dtau(t + mi->h);
-      f.plant = plant;
-      if (mode == CGMRES_B200_MODE_FAST)
-        CU(fast_launch_control(model, ptau_full, f, stream));
-      else
-        CU(onchip_exact_launch_control(model, ptau_full, f, stream));
-      g_launches++;
+      int rc = launch_slice(0, n, plant, dtau(t), dtau(t + mi->h), stream);
+      if (rc) return rc;
       t = t + mi->dt;
       return 0;
     }
@@ -448,11 +476,37 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
   const int nx = h->mi->dim_x, nu = h->mi->dim_u;
   if (!h->soa()) {  // instance-major state == ABI layout: x straight into place, u straight out
     if (n == 0) return 0;
-    CU(cudaMemcpyAsync(h->x, x, sizeof(double) * n * nx, cudaMemcpyHostToDevice, h->stream));
-    int rcu = h->launch_update(0);
-    if (rcu) return rcu;
-    CU(cudaMemcpyAsync(u, h->u_out, sizeof(double) * n * nu, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    const int S = (h->n >= 8192) ? cgmres_b200_controller::kSlices : 1;
+    if (S == 1) {
+      CU(cudaMemcpyAsync(h->x, x, sizeof(double) * n * nx, cudaMemcpyHostToDevice, h->stream));
+      int rcu = h->launch_update(0);
+      if (rcu) return rcu;
+      CU(cudaMemcpyAsync(u, h->u_out, sizeof(double) * n * nu, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      return 0;
+    }
+    // large batches: S slices, each {H2D x, update, D2H u} on its own stream, all ordered after the handle's stream
+    int rcs = h->ensure_side_streams();
+    if (rcs) return rcs;
+    const double dt_t = h->dtau(h->t), dt_th = h->dtau(h->t + h->mi->h);
+    CU(cudaEventRecord(h->ev_begin, h->stream));
+    const int64_t per = (h->n + S - 1) / S;
+    for (int i = 0; i < S; i++) {
+      const int64_t lo = (int64_t)i * per;
+      const int64_t cnt = (lo + per <= h->n) ? per : (h->n - lo);
+      if (cnt <= 0) break;
+      cudaStream_t st = h->side[i];
+      CU(cudaStreamWaitEvent(st, h->ev_begin, 0));
+      CU(cudaMemcpyAsync(h->x + lo * nx, x + lo * nx, sizeof(double) * (size_t)cnt * nx, cudaMemcpyHostToDevice, st));
+      int rcu = h->launch_slice(lo, cnt, 0, dt_t, dt_th, st);
+      if (rcu) return rcu;
+      CU(cudaMemcpyAsync(u + lo * nu, h->u_out + lo * nu, sizeof(double) * (size_t)cnt * nu, cudaMemcpyDeviceToHost,
+                         st));
+      CU(cudaEventRecord(h->ev_done[i], st));
+      CU(cudaStreamWaitEvent(h->stream, h->ev_done[i], 0));  // later work on the handle's stream sees the slices
+    }
+    h->t = h->t + h->mi->dt;
+    for (int i = 0; i < S; i++) CU(cudaEventSynchronize(h->ev_done[i]));
     return 0;
   }
   int rc = h->ensure_stage(n * (size_t)(nx + nu));

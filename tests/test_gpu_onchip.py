@@ -163,3 +163,30 @@ def test_fast_full_size_batch_shard_invariance(cg):
     c2.step_closed_loop(steps)
     assert np.array_equal(c2.get_x(), x_big[lo:hi])
     c2.close()
+
+
+@pytest.mark.parametrize("mode_name", ["MODE_ONCHIP_EXACT", "MODE_FAST"])
+def test_sliced_host_control_equals_device_closed_loop(cg, mode_name):
+    """Large batches take the pipelined path of cgmres_b200_control (4 slices on side streams, copies overlapping
+    kernels).  Instances are independent, so it must give exactly what the device-resident closed loop gives."""
+    mode = getattr(cg, mode_name)
+    model, n, steps = po.MSD, 8200 + 37, 6
+    x0, p, u0 = po.synthetic_batch(model, n, seed=77)
+    a, _ = make(cg, model, x0, p, u0, mode=mode)
+    a.step_closed_loop(steps)
+    b, _ = make(cg, model, x0, p, u0, mode=mode)
+    x = x0.copy()
+    for _ in range(steps):
+        u = b.control(x)
+        cg.plant_step_host(model, x, u)
+    ta, Ua, dUa = a.get_state()
+    tb, Ub, dUb = b.get_state()
+    assert ta == tb
+    if mode == cg.MODE_ONCHIP_EXACT:
+        assert np.array_equal(a.get_x(), x)
+        assert np.array_equal(Ua, Ub) and np.array_equal(dUa, dUb) and np.array_equal(a.get_u(), b.get_u())
+    else:  # the in-kernel plant step of the fast build contracts x + f*dt into an FMA, the host plant does not
+        assert np.abs(a.get_x() - x).max() <= 1e-12
+        assert rel_inf(Ua, Ub) <= 1e-12
+    a.close()
+    b.close()
