@@ -594,6 +594,8 @@ int cgmres_b200_plant_step_host(int model, int64_t n, double* x, const double* u
   return fail(CGMRES_B200_EINVAL, "unknown model");
 }
 
+void cgmres_b200_portable_sincos(double x, double* s, double* c) { ptrig::psincos(x, s, c); }
+
 int64_t cgmres_b200_launch_count(void) { return g_launches.load(); }
 
 }  // extern "C"

@@ -132,6 +132,10 @@ int cgmres_b200_get_status(cgmres_b200_handle h, int32_t* status);
  * same Simulator functor the device epilogue inlines, for callers that drive control() from a non-C++ host. */
 int cgmres_b200_plant_step_host(int model, int64_t n, double* x, const double* u);
 
+/* sin and cos as the arm_type_inverted_pendulum functors evaluate them (include/cgmres_b200/portable_trig.hpp:
+ * +,-,* only, bit-identical on host and device in the exact build modes, <= 1 ulp from glibc); host code */
+void cgmres_b200_portable_sincos(double x, double* s, double* c);
+
 /* kernels launched by this library in this process so far (for the benchmark's launch accounting) */
 int64_t cgmres_b200_launch_count(void);
 

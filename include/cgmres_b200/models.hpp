@@ -15,6 +15,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "cgmres_b200/portable_trig.hpp"
+
 #if defined(__CUDACC__)
 #define CGMRES_HD __host__ __device__ __forceinline__
 #else
@@ -127,12 +129,15 @@ struct ArmPendulumPlantConstants {
   static constexpr double As = 6.25, Bs = 15.6, A52 = 39.1111, C22 = 0.0407448;  // model.hpp:92-98
   static constexpr double A32a = 5.65635, A32 = 0.905016, A32b = 14.1183;
 
-  // sin/cos of (x0-x1) and of x1 are evaluated once per call; every use in the reference
-  // has the same argument, so the values (and hence the results) are the same.
+  // sin/cos of (x0-x1) and of x1 are evaluated once per call; every use in the reference has the same argument,
+  // so the values (and hence the results) are the same.  They come from portable_trig.hpp (pure +,-,*; <= 1 ulp
+  // from glibc) so that host and device agree bit for bit; see that header for what this means for parity.
   template <class X, class U>
   static CGMRES_HD void rhs(double* ret, const X& x, const U& u) {  // model.hpp:37-42 == simulator.hpp:14-19
     const double d = x[0] - x[1];
-    const double sd = sin(d), cd = cos(d), s1 = sin(x[1]);
+    double sd, cd;
+    ptrig::psincos(d, &sd, &cd);
+    const double s1 = ptrig::psin(x[1]);
     ret[0] = x[2];
     ret[1] = x[3];
     ret[2] = -As * x[2] + Bs * u[0];
@@ -165,7 +170,9 @@ struct ArmPendulumModel : SolverDefaults, ArmPendulumPlantConstants {
 
   static CGMRES_HD void dHdx(double* ret, const double* x, const double* u, const double* p, const double* lmd) {
     const double d = x[0] - x[1];
-    const double sd = sin(d), cd = cos(d), c1 = cos(x[1]);  // model.hpp:52-54
+    double sd, cd;
+    ptrig::psincos(d, &sd, &cd);  // model.hpp:52-54
+    const double c1 = ptrig::pcos(x[1]);
     ret[0] = (x[0] - p[0]) * q0 + lmd[3] * (A32 * x[2] * x[2] * cd + A32b * sd * u[0] - A32a * sd * x[2]);
     ret[1] = (x[1] - p[1]) * q1 + lmd[3] * (-A32 * x[2] * x[2] * cd + A52 * c1 - A32b * sd * u[0] + A32a * sd * x[2]);
     ret[2] = x[2] * q2 + lmd[0] - lmd[2] * As + lmd[3] * (0.2e1 * A32 * x[2] * sd + A32a * cd + C22);
@@ -174,7 +181,7 @@ struct ArmPendulumModel : SolverDefaults, ArmPendulumPlantConstants {
 
   // u = [torque, dummy, multiplier]; model.hpp:58-62
   static CGMRES_HD void dHdu(double* ret, const double* x, const double* u, const double*, const double* lmd) {
-    const double cd = cos(x[0] - x[1]);
+    const double cd = ptrig::pcos(x[0] - x[1]);
     ret[0] = (r0 * u[0]) + lmd[2] * Bs - lmd[3] * A32b * cd + (u[2] * (2.0 * u[0] - 2.0 * uc));
     ret[1] = -0.5 * r1 + (2.0 * u[2] * u[1]);
     ret[2] = (u[0] - uc) * (u[0] - uc) + u[1] * u[1] - ur * ur;

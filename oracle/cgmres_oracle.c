@@ -115,6 +115,19 @@ static void msd_huu(double* o, const double* x, const double* u, const double* p
 static void msd_plant(double* o, const double* x, const double* u) { msd_f(o, x, u, NULL); }
 
 /* ---- arm_type_inverted_pendulum: arm_type_inverted_pendulum/model.hpp:5-99 (== multiple_controller/model2.hpp) ---- */
+/* sin/cos: glibc like the reference, or -- in the "ptrig" build of this oracle -- the portable +,-,* implementation
+ * that the GPU's exact modes use, so that those modes can be checked bit for bit on this model too. */
+#ifdef ORACLE_PORTABLE_TRIG
+#include "portable_trig.h"
+#define sin(x) opt_sin(x)
+#define cos(x) opt_cos(x)
+void ORACLE_FN(sincos)(double x, double* s, double* c) { opt_sincos(x, s, c); }
+#else
+void ORACLE_FN(sincos)(double x, double* s, double* c) {
+  *s = sin(x);
+  *c = cos(x);
+}
+#endif
 #define ARM_AS 6.25
 #define ARM_BS 15.6
 #define ARM_A52 39.1111
@@ -175,6 +188,11 @@ static void arm_huu(double* o, const double* x, const double* u, const double* p
 }
 /* arm_type_inverted_pendulum/simulator.hpp:14-19 */
 static void arm_plant(double* o, const double* x, const double* u) { arm_f(o, x, u, NULL); }
+
+#ifdef ORACLE_PORTABLE_TRIG
+#undef sin
+#undef cos
+#endif
 
 /* ---- semiactive_damper: semiactive_damper/model.hpp:4-86 ---- */
 #define SAD_A (-1.0)

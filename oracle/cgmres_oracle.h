@@ -9,6 +9,9 @@
  * Two libraries export this same interface:
  *   oracle/_build/libcgmres_oracle.so   prefix "oracle_"  plain-C restatement
  *                                       (cgmres_oracle.c), kind "port"
+ *   oracle/_build/libcgmres_oracle_ptrig.so  prefix "oraclept_"  the same restatement with the arm model's
+ *                                       sin/cos replaced by oracle/portable_trig.h, kind "port_ptrig": the
+ *                                       bit-exact checker of the GPU's exact modes on the arm model
  *   oracle/_ref/libcgmres_ref.so        prefix "ref_"     the UNMODIFIED reference
  *                                       headers under /root/reference compiled by
  *                                       ref_harness.cpp, kind "reference"
@@ -64,6 +67,10 @@ void ORACLE_FN(get_state)(void* ctl, double* t, double* U, double* dUdt);
 void ORACLE_FN(set_state)(void* ctl, const double* t, const double* U, const double* dUdt);
 /* exit path of the last control(): status = exit code | (columns used << 8) */
 int ORACLE_FN(last_status)(void* ctl);
+
+/* the sin/cos this oracle build evaluates the arm model with (glibc, or the portable one in the ptrig build);
+ * not exported by the reference harness */
+void ORACLE_FN(sincos)(double x, double* s, double* c);
 
 /* x <- x + Simulator::dxdt(x,u)*dt   (main.cpp:74-76 of each example) */
 void ORACLE_FN(plant_step)(int model, double* x, const double* u);

@@ -5,6 +5,7 @@ legs may import this module (see oracle/cgmres_oracle.h).  The product package
 cgmres_cpp_b200 never does.
 
     port = load("port")        # oracle/_build/libcgmres_oracle.so  (C restatement)
+    pt   = load("port_ptrig")  # the same with the arm model's sin/cos from oracle/portable_trig.h
     ref  = load("reference")   # oracle/_ref/libcgmres_ref.so        (unmodified reference headers)
 
 Both expose the same methods; arrays use the reference's own layouts
@@ -72,6 +73,14 @@ class Oracle:
         f("run_closed_loop", C.c_int,
           [C.c_int, C.c_int64, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int,
            _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int])
+        if kind != "reference":
+            f("sincos", None, [C.c_double, _dp, _dp])
+
+    def sincos(self, x: float):
+        """(sin x, cos x) as this oracle build evaluates them inside the arm model."""
+        s, c = C.c_double(), C.c_double()
+        self._sincos(float(x), C.byref(s), C.byref(c))
+        return s.value, c.value
 
     def _fn(self, name, restype, argtypes):
         fn = getattr(self._lib, self._p + name)
@@ -202,6 +211,7 @@ class OracleController:
 
 _PATHS = {
     "port": (os.path.join(HERE, "_build", "libcgmres_oracle.so"), "oracle_"),
+    "port_ptrig": (os.path.join(HERE, "_build", "libcgmres_oracle_ptrig.so"), "oraclept_"),
     "reference": (os.path.join(HERE, "_ref", "libcgmres_ref.so"), "ref_"),
 }
 _CACHE: dict = {}
@@ -221,7 +231,7 @@ def load(kind: str = "port") -> Oracle:
     if kind not in _CACHE:
         path, prefix = _PATHS[kind]
         if not os.path.exists(path):
-            if kind == "port":
+            if kind in ("port", "port_ptrig"):
                 build()
             else:
                 raise FileNotFoundError(f"{path} missing: run `make -C oracle` where /root/reference exists")

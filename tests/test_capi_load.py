@@ -114,3 +114,29 @@ def test_host_plant_step_matches_reference_plant(built, oracle_port):
         got = x.copy()
         cg.plant_step_host(m, got, u)
         assert np.array_equal(got, want), po.MODEL_NAMES[m]
+
+
+def test_portable_trig_host_equals_oracle_restatement_and_is_within_1ulp_of_glibc(built):
+    """The arm model's sin/cos (include/cgmres_b200/portable_trig.hpp, compiled for the host inside the library) must
+    equal the oracle's separate C restatement (oracle/portable_trig.h) bit for bit, and both must stay within
+    1 ulp of glibc -- the only difference between the GPU's exact modes and the reference on the arm model."""
+    import ctypes as C
+
+    import numpy as np
+
+    from cgmres_cpp_b200._lib import lib
+    from oracle import pyoracle as po
+
+    pt, gl = po.load("port_ptrig"), po.load("port")
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.uniform(-0.8, 0.8, 4000), rng.uniform(-7, 7, 4000), rng.uniform(-400, 400, 4000),
+                         rng.uniform(-8e5, 8e5, 2000), [0.0, 3.14159265358979, 0.785398163397448, -0.785398163397449]])
+    worst = 0
+    for x in xs:
+        s, c = C.c_double(), C.c_double()
+        lib().cgmres_b200_portable_sincos(float(x), C.byref(s), C.byref(c))
+        assert (s.value, c.value) == pt.sincos(x), x
+        gs, gc = gl.sincos(x)
+        for a, b in ((s.value, gs), (c.value, gc)):
+            worst = max(worst, abs(int(np.float64(a).view(np.int64)) - int(np.float64(b).view(np.int64))))
+    assert worst <= 1, worst

@@ -332,3 +332,33 @@ def test_multiple_controller_heterogeneous_batch(cg, oracle_best):
     assert np.abs(xb - w2["x_fin"]).max() <= TOL_X_ABS
     for c in (c1, c2, s1, s2):
         c.close()
+
+
+@pytest.mark.parametrize("mode_name", ["MODE_EXACT", "MODE_ONCHIP_EXACT"])
+def test_arm_is_bit_identical_to_the_portable_trig_oracle(cg, mode_name):
+    """arm_type_inverted_pendulum: with sin/cos taken from the portable +,-,* implementation on BOTH sides (the
+    oracle's own C restatement, oracle/portable_trig.h), the exact build modes reproduce the oracle bit for bit --
+    shipped initial condition through the chaotic swing-up for 2000 steps, and a seeded batch for 1000 steps.
+    What separates this oracle from the glibc reference is <= 1 ulp per sin/cos call (tests/test_capi_load.py)."""
+    pt = po.load("port_ptrig")
+    mode = getattr(cg, mode_name)
+    s = po.SHIPPED[po.ARM]
+    want = pt.run_closed_loop(po.ARM, [s["x0"]], [s["p"]], s["u0"], 2000, rec_stride=500, want_U=True)
+    c, _ = make(cg, po.ARM, np.array([s["x0"]]), np.array([s["p"]]), np.array(s["u0"]), mode=mode)
+    for r in range(4):
+        c.step_closed_loop(500)
+        assert np.array_equal(c.get_x(), want["x_traj"][r]), r
+    _, U, dUdt = c.get_state()
+    assert np.array_equal(U, want["U_fin"]) and np.array_equal(dUdt, want["dUdt_fin"])
+    c.close()
+    n = 97
+    x0, p, u0 = po.synthetic_batch(po.ARM, n, seed=808)
+    want = pt.run_closed_loop(po.ARM, x0, p, u0, 1000, want_U=True, n_threads=os.cpu_count() or 4)
+    c, un = make(cg, po.ARM, x0, p, u0, mode=mode)
+    c.step_closed_loop(1000)
+    assert np.array_equal(c.get_x(), want["x_fin"])
+    _, U, dUdt = c.get_state()
+    assert np.array_equal(U, want["U_fin"]) and np.array_equal(dUdt, want["dUdt_fin"])
+    code, ncol = c.get_status()
+    assert (want["exit_hist"].sum(axis=0)[3] == 0) and ((code == 0) | (code == 1)).all()
+    c.close()
