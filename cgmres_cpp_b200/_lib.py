@@ -47,8 +47,10 @@ SIGNATURES = {
     "cgmres_b200_get_status": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_plant_step_host": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "cgmres_b200_portable_sincos": (None, [C.c_double, _dp, _dp]),
+    "cgmres_b200_debug_phase_times": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_launch_count": (C.c_int64, []),
     "cgmres_b200_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
+    "cgmres_b200_measure_fp64_latency": (C.c_int, [C.c_int, C.c_int, _dp]),
 }
 
 _lib = None

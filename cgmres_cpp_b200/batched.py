@@ -208,3 +208,13 @@ def measure_fp64_peak(device: int = 0, use_fma: bool = True) -> float:
     v = C.c_double()
     check(lib().cgmres_b200_measure_fp64_peak(device, int(use_fma), C.byref(v), None))
     return float(v.value)
+
+
+def measure_fp64_latency(device: int = 0) -> dict:
+    """Dependent-issue latency of DFMA / DADD / DMUL in SM cycles."""
+    out = {}
+    for op, name in enumerate(("dfma", "dadd", "dmul")):
+        v = C.c_double()
+        check(lib().cgmres_b200_measure_fp64_latency(device, op, C.byref(v)))
+        out[name] = float(v.value)
+    return out

@@ -80,6 +80,7 @@ struct cgmres_b200_controller {
   double *x = nullptr, *U = nullptr, *dUdt = nullptr, *ptau = nullptr, *F1 = nullptr, *V = nullptr, *xtau = nullptr,
          *u_out = nullptr;
   int32_t* status = nullptr;
+  long long* dbg = nullptr;  // 64 phase timestamps of one warp (debug builds of the on-chip kernel)
   double* stage = nullptr;  // instance-major staging, grown on demand
   size_t stage_doubles = 0;
 
@@ -119,6 +120,7 @@ struct cgmres_b200_controller {
       if ((rc = dalloc(&ptau, l * (size_t)ptau_rows_full()))) return rc;
       if ((rc = dalloc(&u_out, l * mi->dim_u))) return rc;
       if ((rc = dalloc(&status, l))) return rc;
+      if ((rc = dalloc(&dbg, 64))) return rc;
       if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;
       return 0;
     }
@@ -145,6 +147,7 @@ struct cgmres_b200_controller {
     cudaFree(xtau);
     cudaFree(u_out);
     cudaFree(status);
+    cudaFree(dbg);
     cudaFree(stage);
     for (int i = 0; i < kSlices; i++) {
       if (side[i]) cudaStreamDestroy(side[i]);
@@ -178,6 +181,7 @@ struct cgmres_b200_controller {
     f.dtau_t = dt_t;
     f.dtau_th = dt_th;
     f.plant = plant;
+    f.dbg = dbg;
     if (mode == CGMRES_B200_MODE_FAST)
       CU(fast_launch_control(model, ptau_full, f, s));
     else
@@ -595,6 +599,15 @@ int cgmres_b200_plant_step_host(int model, int64_t n, double* x, const double* u
 }
 
 void cgmres_b200_portable_sincos(double x, double* s, double* c) { ptrig::psincos(x, s, c); }
+
+int cgmres_b200_debug_phase_times(cgmres_b200_handle h, int64_t* out64) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!out64 || !h->dbg) return fail(CGMRES_B200_EINVAL, "no phase-timing buffer (exact mode or null pointer)");
+  CU(cudaMemcpyAsync(out64, h->dbg, sizeof(long long) * 64, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 
 int64_t cgmres_b200_launch_count(void) { return g_launches.load(); }
 

@@ -44,6 +44,24 @@ constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved ki
 #endif
 #define CG_PRAGMA(x) _Pragma(#x)
 #define CG_UNROLL(n) CG_PRAGMA(unroll n)
+// phase timestamps of one warp of CTA 0 (debug builds only: -DCG_FAST_TIMING), read back by tools/phase_times.py
+#ifdef CG_FAST_TIMING
+#define CG_MARK(i)                                                                      \
+  do {                                                                                  \
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 32 * 5) a.dbg[(i)] = clock64();      \
+  } while (0)
+#define CG_MARK_SERIAL(i)                                                        \
+  do {                                                                           \
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[(i)] = clock64();    \
+  } while (0)
+#else
+#define CG_MARK(i) \
+  do {             \
+  } while (0)
+#define CG_MARK_SERIAL(i) \
+  do {                    \
+  } while (0)
+#endif
 #ifndef CG_FAST_MAXCTAS
 #define CG_FAST_MAXCTAS 1
 #endif
@@ -362,15 +380,6 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   double* const sc = blk + Y::oS;
   auto inst_blk = [&](int g) { return sm + (size_t)g * Y::stride; };
 
-#ifdef CG_STAGGER_NS
-  // experiment: de-phase the co-resident CTAs of the first wave so one group's serial recursion overlaps the
-  // other group's vector work (they would otherwise start together and stay in lock step)
-  if (blockIdx.x >= gridDim.y * 0 + CG_STAGGER_FIRST && blockIdx.x < 2 * CG_STAGGER_FIRST) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < (long long)CG_STAGGER_NS * 2) {
-    }
-  }
-#endif
   // ---- tensor memory: one allocation, released at the end by the same warp --------------------------------------
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)G * Y::stride);
   if (wid == 0) {
@@ -382,6 +391,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 
+  CG_MARK(1);
   // ---- phase 0: state in.  F1 and B areas <- U, X <- U + h*dUdt (third trajectory), x, p(t) -----------------
   if (has) {
     const double* Ug = a.U + n * (int64_t)L;
@@ -424,6 +434,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   }
   __syncthreads();
 
+  CG_MARK(2);
   // ---- phase 1: the three Krylov-independent F evaluations, one lane per (instance, trajectory), in place ---
   //   A: F(U, x+dx*h, t+h) in the F1 area   B: F(U, x, t) in the B area   C: F(U+h*dUdt, x+dx*h, t+h) in X
   if (threadIdx.x < 3 * n_here) {
@@ -438,6 +449,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   }
   __syncthreads();
 
+  CG_MARK(3);
   // ---- phase 2: b, r0 = b - A*dUdt (F1 stays where trajectory A left it); rho0 -------------------------------
   double w[Q];  // working vector slice (r0, then each new Krylov vector)
   double ssq = 0.0;
@@ -507,10 +519,12 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   if (has && lane == 0) sc[Y::sFLAG] = solving ? 0.0 : 1.0;
 
   // ---- Arnoldi iterations ------------------------------------------------------------------------------------
+  CG_MARK(5);
   // R (packed triangle) and the reflectors are warp-uniform and touched a few times per iteration only: they
   // live in this instance's shared-memory scalars (written by lane 0, read by all lanes after __syncwarp).
 #pragma unroll
   for (int k = 0; k < km; k++) {
+    CG_MARK(10 + 5 * k + 0);
     // X = U + h*v_k (cgmres.hpp:168-169); w currently holds v_k
     if (solving) {
 #pragma unroll
@@ -522,16 +536,20 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         }
       }
     }
+    CG_MARK(10 + 5 * k + 1);
     __syncthreads();
     if (threadIdx.x < n_here) {  // transposed recursions: lane = instance (cgmres.hpp:132-153)
       double* b = inst_blk(threadIdx.x);
       const double* s = b + Y::oS;
       if (s[Y::sFLAG] == 0.0) {
         const double* pf = PFULL ? a.ptau + (n0 + threadIdx.x) * (int64_t)((M::dv + 1) * np) : nullptr;
+        CG_MARK_SERIAL(50 + 2 * k);
         lane_sweep_costates<M>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, a.dtau_th, s + Y::sP, pf);
+        CG_MARK_SERIAL(51 + 2 * k);
       }
     }
     __syncthreads();
+    CG_MARK(10 + 5 * k + 2);
     if (solving) {
       // stage-parallel dHdu (cgmres.hpp:156-161) and (F - F1)*inv_h (cgmres.hpp:173-174), one stage per lane;
       // w_i overwrites u_i in X (same lane reads before it writes): w = A v_k (gmres.hpp:48)
@@ -561,6 +579,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         w[q] = (j < L) ? blk[Y::oX + j] : 0.0;
       }
     }
+    CG_MARK(10 + 5 * k + 3);
     // modified Gram-Schmidt (gmres.hpp:52-58) against v_i, i = 0..k; each v_i slice comes from TMEM once
     double hc[km + 2];
 #pragma unroll
@@ -621,6 +640,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         for (int q = 0; q < Q; q++) w[q] = w[q] * inv;
         basis_store<Q>(tcol(k + 1), w);  // v_{k+1}
       }
+      CG_MARK(10 + 5 * k + 4);
       // stored reflectors on the new column (gmres.hpp:71-77), new reflector (78-85), residual (88-90)
 #pragma unroll
       for (int i = 0; i < k; i++) {
@@ -660,6 +680,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     if (has && lane == 0) sc[Y::sFLAG] = solving ? 0.0 : 1.0;
   }
 
+  CG_MARK(39);
   // ---- back substitution (gmres.hpp:100-107), dUdt += V y (110-111), U += dUdt*dt (cgmres.hpp:102-103) ------
   const bool apply = has && (code == EXIT_FULL || code == EXIT_CONVERGED);
   if (apply) {
@@ -730,6 +751,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     }
   }
 
+  CG_MARK(40);
   // ---- release tensor memory ------------------------------------------------------------------------------------
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

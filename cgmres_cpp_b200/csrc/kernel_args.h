@@ -51,6 +51,7 @@ struct FastArgs {
   int32_t* status;     // [n]
   double dtau_t, dtau_th;
   int plant;
+  long long* dbg;      // phase timestamps (debug builds with -DCG_FAST_TIMING), else unused / null
 };
 
 // on-chip kernels: fast_kernels.cu (FMA, shuffle reductions) and their sequential-sum, no-FMA twin compiled in

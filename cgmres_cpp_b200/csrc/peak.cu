@@ -29,8 +29,54 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
   if (s == 12345.678) out[0] = s;  // keeps the chains alive, practically never stores
 }
 
+// dependent-issue latency of the FP64 pipe: one warp, one chain
+template <int OP>
+__global__ void fp64_latency_kernel(double* out, long long* cycles, int iters, double a, double b) {
+  double r = (double)threadIdx.x * 1e-3 + 1.0;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (OP == 0)
+        r = __fma_rn(r, a, b);
+      else if (OP == 1)
+        r = __dadd_rn(r, b);
+      else
+        r = __dmul_rn(r, a);
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+  if (r == 12345.678) out[0] = r;
+}
+
 }  // namespace
 }  // namespace cgmres_b200
+
+// cycles per dependent FP64 instruction for op = 0 (DFMA), 1 (DADD), 2 (DMUL), measured with one warp on one SM
+extern "C" int cgmres_b200_measure_fp64_latency(int device, int op, double* cycles_per_op) {
+  using namespace cgmres_b200;
+  if (!cycles_per_op || op < 0 || op > 2) return CGMRES_B200_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return CGMRES_B200_ECUDA;
+  double* d = nullptr;
+  long long* c = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess || cudaMalloc(&c, 64) != cudaSuccess) return CGMRES_B200_ECUDA;
+  const int iters = 4096;
+  for (int rep = 0; rep < 2; rep++) {
+    if (op == 0)
+      fp64_latency_kernel<0><<<1, 32>>>(d, c, iters, 0.999999, 1e-9);
+    else if (op == 1)
+      fp64_latency_kernel<1><<<1, 32>>>(d, c, iters, 0.999999, 1e-9);
+    else
+      fp64_latency_kernel<2><<<1, 32>>>(d, c, iters, 0.999999, 1e-9);
+  }
+  long long h = 0;
+  if (cudaMemcpy(&h, c, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return CGMRES_B200_ECUDA;
+  cudaFree(d);
+  cudaFree(c);
+  *cycles_per_op = (double)h / ((double)iters * 16.0);
+  return 0;
+}
 
 extern "C" int cgmres_b200_measure_fp64_peak(int device, int use_fma, double* tflops, double* sm_clock_mhz_hint) {
   using namespace cgmres_b200;

@@ -136,6 +136,10 @@ int cgmres_b200_plant_step_host(int model, int64_t n, double* x, const double* u
  * +,-,* only, bit-identical on host and device in the exact build modes, <= 1 ulp from glibc); host code */
 void cgmres_b200_portable_sincos(double x, double* s, double* c);
 
+/* Debug aid for the on-chip kernel: 64 clock64() phase timestamps of one warp of CTA 0 from the last launch
+ * (all zero unless the library was built with -DCG_FAST_TIMING; tools/phase_times.py decodes them). */
+int cgmres_b200_debug_phase_times(cgmres_b200_handle h, int64_t* out64);
+
 /* kernels launched by this library in this process so far (for the benchmark's launch accounting) */
 int64_t cgmres_b200_launch_count(void);
 
@@ -143,6 +147,9 @@ int64_t cgmres_b200_launch_count(void);
  * DFMA as 2 flop, use_fma=0 issues separate DMUL+DADD (the ceiling of the exact mode).  The roofline denominator
  * of the benchmark (MEASURED_PEAKS.json has no FP64 entry). sm_clock_mhz (may be NULL) = the device's nominal clock. */
 int cgmres_b200_measure_fp64_peak(int device, int use_fma, double* tflops, double* sm_clock_mhz);
+/* dependent-issue latency of the FP64 pipe in SM cycles: op 0 = DFMA, 1 = DADD, 2 = DMUL (one warp, one chain).  The
+ * on-chip kernel is bound by dv-serial recursions, i.e. by this number times their expression depth. */
+int cgmres_b200_measure_fp64_latency(int device, int op, double* cycles_per_op);
 
 #ifdef __cplusplus
 }
