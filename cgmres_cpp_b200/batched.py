@@ -162,6 +162,10 @@ class BatchedCgmres:
     def step_closed_loop(self, n_steps: int = 1):
         check(lib().cgmres_b200_step_closed_loop(self._h, int(n_steps)))
 
+    def set_plant_integrator(self, name: str):
+        """'euler' (the reference's plant step, parity default) or 'rk4' (an extension: the reference has no RK4 to compare with)."""
+        check(lib().cgmres_b200_set_plant_integrator(self._h, {"euler": 1, "rk4": 2}[name]))
+
     def synchronize(self):
         check(lib().cgmres_b200_synchronize(self._h))
 

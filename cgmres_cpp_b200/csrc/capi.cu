@@ -12,6 +12,7 @@
 
 #include "cgmres_b200.h"
 #include "cgmres_b200/models.hpp"
+#include "cgmres_b200/plant.hpp"
 #include "kernel_args.h"
 
 namespace cgmres_b200 {
@@ -77,6 +78,7 @@ struct cgmres_b200_controller {
   cudaEvent_t ev_begin = nullptr, ev_done[kSlices] = {nullptr, nullptr, nullptr, nullptr};
   double t = 0.0;          // cgmres.hpp:195 -- all instances of a handle step in lock step
   bool ptau_full = false;  // false: ptau holds one p per instance (set_ptau_repeat)
+  int integrator = PLANT_EULER;  // plant step of step_closed_loop: the reference's Euler, or RK4
   double *x = nullptr, *U = nullptr, *dUdt = nullptr, *ptau = nullptr, *F1 = nullptr, *V = nullptr, *xtau = nullptr,
          *u_out = nullptr;
   int32_t* status = nullptr;
@@ -259,14 +261,9 @@ struct cgmres_b200_controller {
 #define ON_DEVICE(h) CU(cudaSetDevice((h)->device))
 
 template <class Sim>
-static void plant_host(int64_t n, double* x, const double* u) {
+static void plant_host(int64_t n, double* x, const double* u) {  // Euler: mul(dxdt,dxdt,dt); add(x,x,dxdt)
   constexpr int nx = Sim::dim_x, nu = Sim::dim_u;
-  for (int64_t i = 0; i < n; i++) {
-    double d[nx];
-    Sim::dxdt(d, x + i * nx, u + i * nu);
-    for (int j = 0; j < nx; j++) d[j] = d[j] * Sim::dt;          // mul(dxdt, dxdt, dt)
-    for (int j = 0; j < nx; j++) x[i * nx + j] = x[i * nx + j] + d[j];  // add(x, x, dxdt)
-  }
+  for (int64_t i = 0; i < n; i++) plant_euler<Sim>(x + i * nx, u + i * nu);
 }
 
 extern "C" {
@@ -552,9 +549,17 @@ int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps) {
   ON_DEVICE(h);
   if (n_steps < 0) return fail(CGMRES_B200_EINVAL, "negative step count");
   for (int s = 0; s < n_steps; s++) {
-    int rc = h->launch_update(1);
+    int rc = h->launch_update(h->integrator);
     if (rc) return rc;
   }
+  return 0;
+}
+
+int cgmres_b200_set_plant_integrator(cgmres_b200_handle h, int integrator) {
+  CHECK_H(h);
+  if (integrator != CGMRES_B200_PLANT_EULER && integrator != CGMRES_B200_PLANT_RK4)
+    return fail(CGMRES_B200_EINVAL, "unknown plant integrator");
+  h->integrator = integrator;
   return 0;
 }
 

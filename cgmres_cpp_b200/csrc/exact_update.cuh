@@ -30,6 +30,7 @@
 #include <type_traits>
 
 #include "cgmres_b200/models.hpp"
+#include "cgmres_b200/plant.hpp"
 #include "kernel_args.h"
 
 // Tuning knobs (GPU sweep in profiles/README.md).  The register file is split per SM sub-partition
@@ -570,14 +571,10 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
     a.u_out[(int64_t)j * ld + n] = u0[j];
   }
 
-  if (a.plant) {  // x += Simulator::dxdt(x,u)*dt (<example>/main.cpp:74-76)
-    double f[nx];
-    Sim::dxdt(f, x, u0);
+  if (a.plant) {  // x += Simulator::dxdt(x,u)*dt (<example>/main.cpp:74-76), or the RK4 option (plant.hpp)
+    plant_step<Sim>(a.plant, x, u0);
 #pragma unroll
-    for (int j = 0; j < nx; j++) {
-      double m = f[j] * Sim::dt;
-      a.x[(int64_t)j * ld + n] = x[j] + m;
-    }
+    for (int j = 0; j < nx; j++) a.x[(int64_t)j * ld + n] = x[j];
   }
 #undef WS
   return code | (ncol << 8);

@@ -30,6 +30,7 @@
 #include <stdint.h>
 
 #include "cgmres_b200/models.hpp"
+#include "cgmres_b200/plant.hpp"
 #include "kernel_args.h"
 
 namespace cgmres_b200 {
@@ -736,16 +737,12 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         u0[j] = blk[Y::oX + j];
         a.u_out[n * nu + j] = u0[j];  // cgmres.hpp:109
       }
-      if (a.plant) {  // <example>/main.cpp:74-76
-        double f[nx];
+      if (a.plant) {  // <example>/main.cpp:74-76 (Euler) or the RK4 option, include/cgmres_b200/plant.hpp
 #pragma unroll
         for (int j = 0; j < nx; j++) x[j] = sc[Y::sX + j];
-        Sim::dxdt(f, x, u0);
+        plant_step<Sim>(a.plant, x, u0);
 #pragma unroll
-        for (int j = 0; j < nx; j++) {
-          double m = f[j] * Sim::dt;
-          a.x[n * nx + j] = x[j] + m;
-        }
+        for (int j = 0; j < nx; j++) a.x[n * nx + j] = x[j];
       }
       a.status[n] = code | (ncol << 8);
     }

@@ -36,7 +36,7 @@ struct ExactArgs {
   double* u_out;       // [dim_u][ld]      u = U[0:dim_u]       (cgmres.hpp:109)
   int32_t* status;     // [ld]
   double dtau_t, dtau_th;  // get_dtau(t), get_dtau(t+h) evaluated on the host (cgmres.hpp:32-34)
-  int plant;               // 1: also advance x by one Euler plant step
+  int plant;               // 0: no plant step; 1: Euler (reference); 2: RK4 (include/cgmres_b200/plant.hpp)
 };
 
 // Instance-major device state of the on-chip ("fast") kernels: the layout of the C ABI itself, every instance's

@@ -84,6 +84,10 @@ class Cgmres : public Gmres {
   void step_closed_loop(int n_steps) {
     cgmres_b200::check(cgmres_b200_step_closed_loop(h_, n_steps), "step_closed_loop");
   }
+  // plant integrator of step_closed_loop: CGMRES_B200_PLANT_EULER (reference) or CGMRES_B200_PLANT_RK4
+  void set_plant_integrator(int integrator) {
+    cgmres_b200::check(cgmres_b200_set_plant_integrator(h_, integrator), "set_plant_integrator");
+  }
   void synchronize(void) { cgmres_b200::check(cgmres_b200_synchronize(h_), "synchronize"); }
   void get_state(double* t, double* U, double* dUdt) const {
     cgmres_b200::check(cgmres_b200_get_state(h_, t, U, dUdt), "get_state");

@@ -119,6 +119,12 @@ int cgmres_b200_get_u(cgmres_b200_handle h, double* u);
  * <example>/main.cpp:66-77 (forward Euler).  Asynchronous on the handle's stream. */
 int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps);
 
+/* Plant integrator used by step_closed_loop: EULER (default; what every reference example does) or
+ * classical RK4 on the same Simulator::dxdt with u held over the step (the north star's wording; the reference has
+ * no RK4 to compare with, so this option is excluded from the parity claims). */
+enum { CGMRES_B200_PLANT_EULER = 1, CGMRES_B200_PLANT_RK4 = 2 };
+int cgmres_b200_set_plant_integrator(cgmres_b200_handle h, int integrator);
+
 /* checkpoint / teacher forcing: the complete controller state {t, U, dUdt} (cgmres.hpp:195-197).
  * Any array pointer may be NULL.  U, dUdt: [n][dv*dim_u] host. */
 int cgmres_b200_get_state(cgmres_b200_handle h, double* t, double* U, double* dUdt);

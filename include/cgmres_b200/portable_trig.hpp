@@ -4,9 +4,9 @@
 // Why: arm_type_inverted_pendulum/model.hpp calls libm sin/cos.  CUDA's and glibc's implementations are both
 // accurate to < 1 ulp but round differently on a few % of arguments, and the pendulum swing-up amplifies a 1-ulp
 // difference past 1e-6 within ~1100 closed-loop steps.  With this header the exact build
-// modes are bit-reproducible for the arm model too: the CPU oracle has its own C restatement of the same
-// algorithm (oracle/portable_trig.h) and the GPU must match it bit for bit; the distance between this
-// implementation and glibc's (<= 1 ulp, tests/test_oracle.py) is what remains between the GPU and the
+// modes are bit-reproducible for the arm model too: the CPU checker of the test suite has its own C restatement
+// of the same algorithm and the GPU must match it bit for bit; the distance between this implementation and
+// glibc's (<= 1 ulp, measured in tests/test_capi_load.py) is what remains between the GPU and the
 // reference-with-glibc, and is held to the north-star tolerances over 1000 steps.
 //
 // Algorithm: the classic fdlibm scheme (Sun Microsystems, "freely granted" licence): Cody-Waite reduction by

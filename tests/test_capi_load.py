@@ -58,10 +58,9 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text, (dirpath, f)
-    for f in os.listdir(os.path.join(ROOT, "include")):
-        p = os.path.join(ROOT, "include", f)
-        if os.path.isfile(p):
-            assert "oracle" not in open(p).read().lower(), f
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
+        for f in files:
+            assert "oracle" not in open(os.path.join(dirpath, f)).read().lower(), (dirpath, f)
 
 
 def test_cpp_dropin_header_compiles_with_host_compiler(built, tmp_path):

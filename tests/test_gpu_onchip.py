@@ -190,3 +190,33 @@ def test_sliced_host_control_equals_device_closed_loop(cg, mode_name):
         assert rel_inf(Ua, Ub) <= 1e-12
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("mode_name", ["MODE_EXACT", "MODE_ONCHIP_EXACT", "MODE_FAST"])
+def test_rk4_plant_option(cg, mode_name):
+    """The optional on-device RK4 plant (north star item 5; the reference only has Euler, so there is no reference
+    oracle): one closed-loop step must equal control() + an independent numpy RK4 of the same plant equations."""
+    mode = getattr(cg, mode_name)
+    model, n = po.SEMIACTIVE, 50
+    x0, p, u0 = po.synthetic_batch(model, n, seed=9)
+    a, _ = make(cg, model, x0, p, u0, mode=mode)
+    a.set_plant_integrator("rk4")
+    b, _ = make(cg, model, x0, p, u0, mode=mode)
+    x = x0.copy()
+    dt = 0.001
+
+    def f(x, u):  # semiactive_damper/simulator.hpp:13-16
+        return np.stack([x[:, 1], -1.0 * x[:, 0] + -1.0 * u[:, 0] * x[:, 1]], axis=1)
+
+    for _ in range(20):
+        a.step_closed_loop(1)
+        u = b.control(x)
+        k1 = f(x, u)
+        k2 = f(x + 0.5 * dt * k1, u)
+        k3 = f(x + 0.5 * dt * k2, u)
+        k4 = f(x + dt * k3, u)
+        x = x + dt / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+        assert np.abs(a.get_x() - x).max() <= 1e-13
+    a.set_plant_integrator("euler")
+    a.close()
+    b.close()
