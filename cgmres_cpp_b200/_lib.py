@@ -42,6 +42,8 @@ SIGNATURES = {
     "cgmres_b200_get_x": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_get_u": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_step_closed_loop": (C.c_int, [_h, C.c_int]),
+    "cgmres_b200_set_t": (C.c_int, [_h, C.c_void_p]),
+    "cgmres_b200_get_t": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_set_plant_integrator": (C.c_int, [_h, C.c_int]),
     "cgmres_b200_get_state": (C.c_int, [_h, _dp, C.c_void_p, C.c_void_p]),
     "cgmres_b200_set_state": (C.c_int, [_h, _dp, C.c_void_p, C.c_void_p]),

@@ -162,6 +162,16 @@ class BatchedCgmres:
     def step_closed_loop(self, n_steps: int = 1):
         check(lib().cgmres_b200_step_closed_loop(self._h, int(n_steps)))
 
+    def set_t(self, t):
+        """Per-instance controller clocks t[n] (None: back to the batch-uniform clock)."""
+        a = None if t is None else _f64(t, (self.n,))
+        check(lib().cgmres_b200_set_t(self._h, _ptr(a)))
+
+    def get_t(self):
+        t = np.empty(self.n)
+        check(lib().cgmres_b200_get_t(self._h, _ptr(t)))
+        return t
+
     def set_plant_integrator(self, name: str):
         """'euler' (the reference's plant step, parity default) or 'rk4' (an extension: the reference has no RK4 to compare with)."""
         check(lib().cgmres_b200_set_plant_integrator(self._h, {"euler": 1, "rk4": 2}[name]))

@@ -82,6 +82,7 @@ struct cgmres_b200_controller {
   double *x = nullptr, *U = nullptr, *dUdt = nullptr, *ptau = nullptr, *F1 = nullptr, *V = nullptr, *xtau = nullptr,
          *u_out = nullptr;
   int32_t* status = nullptr;
+  double* t_inst = nullptr;  // per-instance controller clocks (set_t); null = lock step with `t`
   long long* dbg = nullptr;  // 64 phase timestamps of one warp (debug builds of the on-chip kernel)
   double* stage = nullptr;  // instance-major staging, grown on demand
   size_t stage_doubles = 0;
@@ -149,6 +150,7 @@ struct cgmres_b200_controller {
     cudaFree(xtau);
     cudaFree(u_out);
     cudaFree(status);
+    cudaFree(t_inst);
     cudaFree(dbg);
     cudaFree(stage);
     for (int i = 0; i < kSlices; i++) {
@@ -182,6 +184,7 @@ struct cgmres_b200_controller {
     f.status = status + lo;
     f.dtau_t = dt_t;
     f.dtau_th = dt_th;
+    f.t_inst = t_inst ? t_inst + lo : nullptr;
     f.plant = plant;
     f.dbg = dbg;
     if (mode == CGMRES_B200_MODE_FAST)
@@ -216,6 +219,7 @@ struct cgmres_b200_controller {
     a.status = status;
     a.dtau_t = dtau(t);
     a.dtau_th = dtau(t + mi->h);
+    a.t_inst = t_inst;
     a.plant = plant;
     CU(exact_launch_control(model, ptau_full, a, stream));
     g_launches++;
@@ -552,6 +556,34 @@ int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps) {
     int rc = h->launch_update(h->integrator);
     if (rc) return rc;
   }
+  return 0;
+}
+
+int cgmres_b200_set_t(cgmres_b200_handle h, const double* t) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  CU(cudaStreamSynchronize(h->stream));
+  if (!t) {  // back to lock step
+    if (h->t_inst) CU(cudaFree(h->t_inst));
+    h->t_inst = nullptr;
+    return 0;
+  }
+  if (!h->t_inst) CU(cudaMalloc(&h->t_inst, sizeof(double) * (size_t)(h->ld ? h->ld : 1)));
+  CU(cudaMemcpyAsync(h->t_inst, t, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cgmres_b200_get_t(cgmres_b200_handle h, double* t) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (!t) return fail(CGMRES_B200_EINVAL, "t is null");
+  if (!h->t_inst) {
+    for (int64_t i = 0; i < h->n; i++) t[i] = h->t;
+    return 0;
+  }
+  CU(cudaMemcpyAsync(t, h->t_inst, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -193,7 +193,8 @@ __device__ __forceinline__ void sweep_w(const ExactArgs& a, const int64_t n, con
 // U and dUdt are read once per direction instead of three times and b / F1 are consumed from registers.
 template <class M, bool PFULL>
 __device__ __forceinline__ void sweep_first3(const ExactArgs& a, const int64_t n, const double* x, const double* xh,
-                                             double* __restrict__ r0out, const double* pconst) {
+                                             double* __restrict__ r0out, const double* pconst, const double dtau_t,
+                                             const double dtau_th) {
   using S = Sz<M>;
   constexpr int nx = S::nx, nu = S::nu, np = S::np, dv = S::dv;
   const int64_t ld = a.ld;
@@ -205,7 +206,7 @@ __device__ __forceinline__ void sweep_first3(const ExactArgs& a, const int64_t n
   double* __restrict__ xtB = xtA + plane;
   double* __restrict__ xtC = xtB + plane;
   const double* __restrict__ pt = a.ptau + n;
-  const double dth = a.dtau_th, dt0 = a.dtau_t;
+  const double dth = dtau_th, dt0 = dtau_t;
   constexpr double hh = M::h;
   constexpr double inv_h = 1.0 / M::h;
   constexpr double c1 = (1 - M::zeta * M::h);
@@ -361,7 +362,16 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
   double* V = a.V + n;
   auto col = [&](int k) { return V + (int64_t)k * L * ld; };
 
-  sweep_first3<M, PFULL>(a, n, x, xh, col(0), pc);  // F1, b and r0 = b - A*dUdt in one pair of sweeps
+  // horizon steps: batch-uniform (host libm, bit-identical to the reference) or from this instance's own clock
+  double dtau_t = a.dtau_t, dtau_th = a.dtau_th;
+  if (a.t_inst) {
+    const double ti = a.t_inst[n];
+    dtau_t = horizon_dtau<M>(ti);
+    dtau_th = horizon_dtau<M>(ti + M::h);
+    a.t_inst[n] = ti + M::dt;  // cgmres.hpp:107
+  }
+
+  sweep_first3<M, PFULL>(a, n, x, xh, col(0), pc, dtau_t, dtau_th);  // F1, b, r0 = b - A*dUdt in one pair of sweeps
 
   int code = EXIT_FULL;
   int ncol = 0;
@@ -393,7 +403,7 @@ __device__ __forceinline__ int control_update(const ExactArgs& a, const int64_t 
     int k = 0;
     for (; k < km; k++) {
       double* w = col(k + 1);
-      sweep_w<M, PFULL>(a, n, xh, a.dtau_th, col(k), WS(W::VS + k), w, pc);  // w = A v_k (gmres.hpp:48)
+      sweep_w<M, PFULL>(a, n, xh, dtau_th, col(k), WS(W::VS + k), w, pc);  // w = A v_k (gmres.hpp:48)
 
       // modified Gram-Schmidt (gmres.hpp:52-58); h_ik kept in HC[i]
       {

@@ -99,7 +99,8 @@ struct Lay {
   static constexpr int sX = sG + 3 * km;               // x
   static constexpr int sXH = sX + nx;                  // x + dxdt*h
   static constexpr int sP = sXH + nx;                  // p(t) (repeat mode) / first stage
-  static constexpr int sRED = sP + np1;                // reduction result slot (EXACT_SUMS)
+  static constexpr int sDT = sP + np1;                 // dtau(t), dtau(t+h) of this instance
+  static constexpr int sRED = sDT + 2;                 // reduction result slot (EXACT_SUMS)
   static constexpr int sFLAG = sRED + 1;               // state: 0 solving, else finished (as double)
   static constexpr int sCount = sFLAG + 1;
   static constexpr int raw = oS + sCount;
@@ -410,7 +411,18 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     }
     if (lane < nx) sc[Y::sX + lane] = a.x[n * nx + lane];
     if (lane < np) sc[Y::sP + lane] = a.ptau[n * (int64_t)(PFULL ? (M::dv + 1) * np : np) + lane];
-    if (lane == 0) sc[Y::sFLAG] = 0.0;
+    if (lane == 0) {
+      sc[Y::sFLAG] = 0.0;
+      if (a.t_inst) {  // controllers started at different times: per-instance clock, horizon ramp on the device
+        const double ti = a.t_inst[n];
+        sc[Y::sDT] = horizon_dtau<M>(ti);
+        sc[Y::sDT + 1] = horizon_dtau<M>(ti + hh);
+        a.t_inst[n] = ti + M::dt;  // cgmres.hpp:107
+      } else {
+        sc[Y::sDT] = a.dtau_t;
+        sc[Y::sDT + 1] = a.dtau_th;
+      }
+    }
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     const double* pf = PFULL ? a.ptau + (n0 + g) * (int64_t)((M::dv + 1) * np) : nullptr;
     double* io = b + (tr == 0 ? Y::oF1 : (tr == 1 ? Y::oB : Y::oX));
     double* plane = b + (tr == 0 ? Y::oXT : (tr == 1 ? Y::oXTB : Y::oXTC));
-    lane_sweep_full<M>(io, io, plane, tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? a.dtau_t : a.dtau_th, s + Y::sP,
+    lane_sweep_full<M>(io, io, plane, tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? s[Y::sDT] : s[Y::sDT + 1], s + Y::sP,
                        pf);
   }
   __syncthreads();
@@ -545,7 +557,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
       if (s[Y::sFLAG] == 0.0) {
         const double* pf = PFULL ? a.ptau + (n0 + threadIdx.x) * (int64_t)((M::dv + 1) * np) : nullptr;
         CG_MARK_SERIAL(50 + 2 * k);
-        lane_sweep_costates<M>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, a.dtau_th, s + Y::sP, pf);
+        lane_sweep_costates<M>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, s[Y::sDT + 1], s + Y::sP, pf);
         CG_MARK_SERIAL(51 + 2 * k);
       }
     }

@@ -36,6 +36,7 @@ struct ExactArgs {
   double* u_out;       // [dim_u][ld]      u = U[0:dim_u]       (cgmres.hpp:109)
   int32_t* status;     // [ld]
   double dtau_t, dtau_th;  // get_dtau(t), get_dtau(t+h) evaluated on the host (cgmres.hpp:32-34)
+  double* t_inst;          // null: all instances share the handle's clock; else per-instance t [n], advanced by dt
   int plant;               // 0: no plant step; 1: Euler (reference); 2: RK4 (include/cgmres_b200/plant.hpp)
 };
 
@@ -50,6 +51,7 @@ struct FastArgs {
   double* u_out;       // [n][dim_u]
   int32_t* status;     // [n]
   double dtau_t, dtau_th;
+  double* t_inst;      // null: lock step (dtau from the host); else per-instance clocks [n], dtau evaluated on device
   int plant;
   long long* dbg;      // phase timestamps (debug builds with -DCG_FAST_TIMING), else unused / null
 };

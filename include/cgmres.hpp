@@ -84,6 +84,9 @@ class Cgmres : public Gmres {
   void step_closed_loop(int n_steps) {
     cgmres_b200::check(cgmres_b200_step_closed_loop(h_, n_steps), "step_closed_loop");
   }
+  // per-instance controller clocks t[n] (nullptr: back to the batch-uniform clock)
+  void set_t(const double* t) { cgmres_b200::check(cgmres_b200_set_t(h_, t), "set_t"); }
+  void get_t(double* t) const { cgmres_b200::check(cgmres_b200_get_t(h_, t), "get_t"); }
   // plant integrator of step_closed_loop: CGMRES_B200_PLANT_EULER (reference) or CGMRES_B200_PLANT_RK4
   void set_plant_integrator(int integrator) {
     cgmres_b200::check(cgmres_b200_set_plant_integrator(h_, integrator), "set_plant_integrator");

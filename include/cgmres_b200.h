@@ -119,6 +119,14 @@ int cgmres_b200_get_u(cgmres_b200_handle h, double* u);
  * <example>/main.cpp:66-77 (forward Euler).  Asynchronous on the handle's stream. */
 int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps);
 
+/* Per-instance controller clocks (controllers started at different times): t[n] host.  From then on
+ * every instance evaluates its own horizon step get_dtau(t_i), get_dtau(t_i + h) on the device (CUDA exp: within
+ * 1 ulp of the host libm, so results follow the reference to the tolerance bars rather than bit for bit) and
+ * advances t_i by dt per update.  t = NULL returns to the batch-uniform clock of get_state/set_state, whose horizon
+ * steps are computed on the host and are bit-identical to the reference's. */
+int cgmres_b200_set_t(cgmres_b200_handle h, const double* t);
+int cgmres_b200_get_t(cgmres_b200_handle h, double* t);
+
 /* Plant integrator used by step_closed_loop: EULER (default; what every reference example does) or
  * classical RK4 on the same Simulator::dxdt with u held over the step (the north star's wording; the reference has
  * no RK4 to compare with, so this option is excluded from the parity claims). */

@@ -35,6 +35,12 @@ struct SolverDefaults {
   static constexpr uint16_t k_max = 5;    // GMRES iterations
 };
 
+// Horizon step of the C/GMRES continuation, cgmres.hpp:32-34: dtau(t) = Tf*(1 - exp(-alpha*t))/dv.
+template <class M>
+CGMRES_HD double horizon_dtau(double t) {
+  return M::Tf * (1 - exp(-M::alpha * t)) / (double)M::dv;
+}
+
 // ---------------------------------------------------------------------------
 // Two-mass spring/damper chain, two bounded forces.
 // reference: mass_spring_damper/model.hpp (and multiple_controller/model1.hpp)

@@ -220,3 +220,35 @@ def test_rk4_plant_option(cg, mode_name):
     a.set_plant_integrator("euler")
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("mode_name", ["MODE_EXACT", "MODE_ONCHIP_EXACT", "MODE_FAST"])
+def test_per_instance_start_times(cg, oracle_port, mode_name):
+    """Controllers started at different times: each instance carries its own clock t_i, so its
+    horizon step dtau(t_i) differs.  The oracle runs every instance as its own object with its own t; the device
+    evaluates exp() itself (<= 1 ulp from glibc), hence the tolerance bars instead of bit equality."""
+    mode = getattr(cg, mode_name)
+    model, n, steps = po.MSD, 21, 150
+    x0, p, u0 = po.synthetic_batch(model, n, seed=17)
+    # staggered starts within 10 ms: the continuation method needs U consistent with the horizon length, so a
+    # controller initialised by init_u0_newton cannot be dropped at a large t (the reference diverges there too)
+    t0 = np.linspace(0.0, 0.01, n)
+    c, un = make(cg, model, x0, p, u0, mode=mode)
+    c.set_t(t0)
+    c.step_closed_loop(steps)
+    x = c.get_x()
+    _, U, _ = c.get_state(want_dUdt=False)
+    assert np.allclose(c.get_t(), t0 + steps * c.dt, rtol=0, atol=1e-12)
+    for i in range(n):
+        k = oracle_port.controller(model)
+        k.set_ptau_repeat(p[i])
+        k.init_u0_newton(u0, x0[i], p[i], 10)
+        k.set_state(t=float(t0[i]))
+        xi = x0[i].copy()
+        for _ in range(steps):
+            oracle_port.plant_step(model, xi, k.control(xi))
+        assert np.abs(x[i] - xi).max() <= TOL_X_ABS, (i, np.abs(x[i] - xi).max())
+        assert rel_inf(U[i][None], k.get_state()[1][None]) <= 1e-6
+    c.set_t(None)  # back to the uniform clock
+    c.step_closed_loop(1)
+    c.close()
