@@ -252,3 +252,25 @@ def test_per_instance_start_times(cg, oracle_port, mode_name):
     c.set_t(None)  # back to the uniform clock
     c.step_closed_loop(1)
     c.close()
+
+
+def test_concurrent_onchip_handles_share_tensor_memory(cg):
+    """Two on-chip handles of different models stepping concurrently on their own streams: their CTAs can be
+    co-resident on an SM and both allocate tensor memory (tcgen05.alloc blocks until columns are free).  Results
+    must equal the stand-alone runs; the test would hang (pytest-timeout / driver limit) on an allocation deadlock."""
+    n1, n2, steps = 3000, 5000, 40
+    x1, p1, u1 = po.synthetic_batch(po.MSD, n1, seed=21)
+    x2, p2, u2 = po.synthetic_batch(po.SEMIACTIVE, n2, seed=22)
+    a1, _ = make(cg, po.MSD, x1, p1, u1, mode=cg.MODE_ONCHIP_EXACT)
+    a2, _ = make(cg, po.SEMIACTIVE, x2, p2, u2, mode=cg.MODE_ONCHIP_EXACT)
+    for _ in range(steps):
+        a1.step_closed_loop(1)
+        a2.step_closed_loop(1)
+    xa, xb = a1.get_x(), a2.get_x()
+    b1, _ = make(cg, po.MSD, x1, p1, u1, mode=cg.MODE_ONCHIP_EXACT)
+    b1.step_closed_loop(steps)
+    b2, _ = make(cg, po.SEMIACTIVE, x2, p2, u2, mode=cg.MODE_ONCHIP_EXACT)
+    b2.step_closed_loop(steps)
+    assert np.array_equal(xa, b1.get_x()) and np.array_equal(xb, b2.get_x())
+    for c in (a1, a2, b1, b2):
+        c.close()
