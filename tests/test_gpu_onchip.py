@@ -274,3 +274,35 @@ def test_concurrent_onchip_handles_share_tensor_memory(cg):
     assert np.array_equal(xa, b1.get_x()) and np.array_equal(xb, b2.get_x())
     for c in (a1, a2, b1, b2):
         c.close()
+
+
+@pytest.mark.parametrize("mode_name", ["MODE_EXACT", "MODE_ONCHIP_EXACT"])
+def test_device_pointer_control_on_a_caller_stream(cg, oracle_best, mode_name):
+    """cgmres_b200_control_dev: x and u stay in device memory (instance-major), the handle runs on the caller's
+    stream (cgmres_b200_set_stream) -- here torch tensors on a torch stream; results bit-identical to the oracle."""
+    import torch
+
+    mode = getattr(cg, mode_name)
+    model, n, steps = po.MSD, 70, 25
+    x0, p, u0 = po.synthetic_batch(model, n, seed=41)
+    want = oracle_best.run_closed_loop(model, x0, p, u0, steps, want_U=True)
+    c, _ = make(cg, model, x0, p, u0, mode=mode)
+    stream = torch.cuda.Stream()
+    c.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        xd = torch.from_numpy(x0).cuda()
+        ud = torch.empty((n, c.dim_u), dtype=torch.float64, device="cuda")
+        dt = 0.001
+        for _ in range(steps):
+            c.control_dev(ud.data_ptr(), xd.data_ptr())
+            # plant on the device in the reference's operation order (mass_spring_damper/simulator.hpp:13-18)
+            f2 = (((-1.0 * xd[:, 0] + 1.0 * xd[:, 1]) - 2.0 * xd[:, 2]) + 1.0 * xd[:, 3]) + ud[:, 0]
+            f3 = (((1.0 * xd[:, 0] - 1.0 * xd[:, 1]) + 1.0 * xd[:, 2]) - 1.0 * xd[:, 3]) + ud[:, 1]
+            xn = torch.stack([xd[:, 0] + xd[:, 2] * dt, xd[:, 1] + xd[:, 3] * dt, xd[:, 2] + f2 * dt,
+                              xd[:, 3] + f3 * dt], dim=1)
+            xd = xn.contiguous()
+        stream.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), want["x_fin"])
+    assert np.array_equal(c.get_state()[1], want["U_fin"])
+    c.set_stream(None)
+    c.close()
