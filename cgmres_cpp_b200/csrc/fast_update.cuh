@@ -256,12 +256,16 @@ __device__ __forceinline__ void basis_load(uint32_t taddr, double* v) {
 
 // Forward Euler rollout of one instance by ONE lane (cgmres.hpp:132-140): returns xtau[dv] in xc, stores
 // xtau[1..dv-1] to the scratch plane xt.
-template <class M>
-__device__ __forceinline__ void lane_rollout(const double* in, double* xt, const double* x0, const double dtau,
-                                             const double* pconst, const double* pfull, double* xc) {
+template <class M, bool PFULL>
+__device__ __forceinline__ void lane_rollout(const double* __restrict__ in, double* __restrict__ xt,
+                                             const double* __restrict__ x0, const double dtau,
+                                             const double* __restrict__ pconst, const double* __restrict__ pfull,
+                                             double* __restrict__ xc) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
   double u[nu], p[Y::np1];
+#pragma unroll
+  for (int j = 0; j < np; j++) p[j] = pconst[j];  // constant reference (set_ptau_repeat); PFULL reloads per stage
 #pragma unroll
   for (int j = 0; j < nx; j++) xc[j] = x0[j];
 CG_UNROLL(CG_SWEEP_UNROLL)
@@ -269,8 +273,10 @@ CG_UNROLL(CG_SWEEP_UNROLL)
     double f[nx];
 #pragma unroll
     for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+    if (PFULL) {
 #pragma unroll
-    for (int j = 0; j < np; j++) p[j] = pfull ? pfull[i * np + j] : pconst[j];
+      for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
+    }
     M::dxdt(f, xc, u, p);
 #pragma unroll
     for (int j = 0; j < nx; j++) {
@@ -286,15 +292,21 @@ CG_UNROLL(CG_SWEEP_UNROLL)
 
 // Full sweep with dHdu inside (used for the three Krylov-independent evaluations, where 3 lanes per instance
 // are busy): out[i] = dHdu(x_i, u_i, p_i, lambda_{i+1})   (cgmres.hpp:113-162)
-template <class M>
-__device__ __forceinline__ void lane_sweep_full(const double* in, double* out, double* xt, const double* x0,
-                                                const double dtau, const double* pconst, const double* pfull) {
+template <class M, bool PFULL>
+__device__ __forceinline__ void lane_sweep_full(const double* in, double* out, double* __restrict__ xt,
+                                                const double* __restrict__ x0, const double dtau,
+                                                const double* __restrict__ pconst,
+                                                const double* __restrict__ pfull) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
   double xc[nx], lmd[nx], u[nu], p[Y::np1];
-  lane_rollout<M>(in, xt, x0, dtau, pconst, pfull, xc);
 #pragma unroll
-  for (int j = 0; j < np; j++) p[j] = pfull ? pfull[dv * np + j] : pconst[j];
+  for (int j = 0; j < np; j++) p[j] = pconst[j];
+  lane_rollout<M, PFULL>(in, xt, x0, dtau, pconst, pfull, xc);
+  if (PFULL) {
+#pragma unroll
+    for (int j = 0; j < np; j++) p[j] = pfull[dv * np + j];
+  }
   M::dPhidx(lmd, xc, p);  // cgmres.hpp:145
 CG_UNROLL(CG_SWEEP_UNROLL)
   for (int i = dv - 1; i >= 0; i--) {  // cgmres.hpp:146-161
@@ -303,8 +315,10 @@ CG_UNROLL(CG_SWEEP_UNROLL)
     for (int j = 0; j < nx; j++) xi[j] = (i > 0) ? xt[(i - 1) * nx + j] : x0[j];
 #pragma unroll
     for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+    if (PFULL) {
 #pragma unroll
-    for (int j = 0; j < np; j++) p[j] = pfull ? pfull[i * np + j] : pconst[j];
+      for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
+    }
     M::dHdu(hu, xi, u, p, lmd);
 #pragma unroll
     for (int j = 0; j < nu; j++) out[i * nu + j] = hu[j];
@@ -322,15 +336,23 @@ CG_UNROLL(CG_SWEEP_UNROLL)
 // Arnoldi sweeps: the serial lane only runs the two recursions (rollout and costate) and leaves the costates
 // lt[i] = ltau[i+1], i = 0..dv-1; the stage-parallel dHdu (cgmres.hpp:156-161) is evaluated afterwards by the
 // owning warp, one stage per lane.  This takes ~40 % of the instructions off the serial critical path.
-template <class M>
-__device__ __forceinline__ void lane_sweep_costates(const double* in, double* xt, double* lt, const double* x0,
-                                                    const double dtau, const double* pconst, const double* pfull) {
+template <class M, bool PFULL>
+// (in, xt and lt never overlap: __restrict__ lets the compiler hoist the next stages' loads above this stage's
+//  stores, which takes the shared-memory latency off the recursion's critical path)
+__device__ __forceinline__ void lane_sweep_costates(const double* __restrict__ in, double* __restrict__ xt,
+                                                    double* __restrict__ lt, const double* __restrict__ x0,
+                                                    const double dtau, const double* __restrict__ pconst,
+                                                    const double* __restrict__ pfull) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
   double xc[nx], lmd[nx], u[nu], p[Y::np1];
-  lane_rollout<M>(in, xt, x0, dtau, pconst, pfull, xc);
 #pragma unroll
-  for (int j = 0; j < np; j++) p[j] = pfull ? pfull[dv * np + j] : pconst[j];
+  for (int j = 0; j < np; j++) p[j] = pconst[j];
+  lane_rollout<M, PFULL>(in, xt, x0, dtau, pconst, pfull, xc);
+  if (PFULL) {
+#pragma unroll
+    for (int j = 0; j < np; j++) p[j] = pfull[dv * np + j];
+  }
   M::dPhidx(lmd, xc, p);
 #pragma unroll
   for (int j = 0; j < nx; j++) lt[(dv - 1) * nx + j] = lmd[j];
@@ -341,8 +363,10 @@ CG_UNROLL(CG_SWEEP_UNROLL)
     for (int j = 0; j < nx; j++) xi[j] = xt[(i - 1) * nx + j];
 #pragma unroll
     for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+    if (PFULL) {
 #pragma unroll
-    for (int j = 0; j < np; j++) p[j] = pfull ? pfull[i * np + j] : pconst[j];
+      for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
+    }
     M::dHdx(hx, xi, u, p, lmd);
 #pragma unroll
     for (int j = 0; j < nx; j++) {
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     const double* pf = PFULL ? a.ptau + (n0 + g) * (int64_t)((M::dv + 1) * np) : nullptr;
     double* io = b + (tr == 0 ? Y::oF1 : (tr == 1 ? Y::oB : Y::oX));
     double* plane = b + (tr == 0 ? Y::oXT : (tr == 1 ? Y::oXTB : Y::oXTC));
-    lane_sweep_full<M>(io, io, plane, tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? s[Y::sDT] : s[Y::sDT + 1], s + Y::sP,
+    lane_sweep_full<M, PFULL>(io, io, plane, tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? s[Y::sDT] : s[Y::sDT + 1], s + Y::sP,
                        pf);
   }
   __syncthreads();
@@ -557,7 +581,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
       if (s[Y::sFLAG] == 0.0) {
         const double* pf = PFULL ? a.ptau + (n0 + threadIdx.x) * (int64_t)((M::dv + 1) * np) : nullptr;
         CG_MARK_SERIAL(50 + 2 * k);
-        lane_sweep_costates<M>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, s[Y::sDT + 1], s + Y::sP, pf);
+        lane_sweep_costates<M, PFULL>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, s[Y::sDT + 1], s + Y::sP, pf);
         CG_MARK_SERIAL(51 + 2 * k);
       }
     }
