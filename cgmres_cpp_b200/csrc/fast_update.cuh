@@ -420,17 +420,25 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
   CG_MARK(1);
   // ---- phase 0: state in.  F1 and B areas <- U, X <- U + h*dUdt (third trajectory), x, p(t) -----------------
   if (has) {
-    const double* Ug = a.U + n * (int64_t)L;
-    const double* dUg = a.dUdt + n * (int64_t)L;
+    const double* __restrict__ Ug = a.U + n * (int64_t)L;
+    const double* __restrict__ dUg = a.dUdt + n * (int64_t)L;
+    // all global loads first (the compiler cannot prove that the generic-pointer loads do not alias the
+    // shared-memory stores, and would otherwise serialise Q HBM round trips), then the stores
+    double uu[Q], dd[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const int j = lane + 32 * q;
+      uu[q] = (j < L) ? Ug[j] : 0.0;
+      dd[q] = (j < L) ? dUg[j] : 0.0;
+    }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       const int j = lane + 32 * q;
       if (j < L) {
-        const double uu = Ug[j];
-        blk[Y::oF1 + j] = uu;
-        blk[Y::oB + j] = uu;
-        double v = dUg[j] * hh;  // cgmres.hpp:168-169
-        blk[Y::oX + j] = v + uu;
+        blk[Y::oF1 + j] = uu[q];
+        blk[Y::oB + j] = uu[q];
+        double v = dd[q] * hh;  // cgmres.hpp:168-169
+        blk[Y::oX + j] = v + uu[q];
       }
     }
     if (lane < nx) sc[Y::sX + lane] = a.x[n * nx + lane];
@@ -564,12 +572,18 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     CG_MARK(10 + 5 * k + 0);
     // X = U + h*v_k (cgmres.hpp:168-169); w currently holds v_k
     if (solving) {
+      double uu[Q];  // U from L2: loads first, then the shared-memory stores (see phase 0)
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        const int j = lane + 32 * q;
+        uu[q] = (j < L) ? a.U[n * (int64_t)L + j] : 0.0;
+      }
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int j = lane + 32 * q;
         if (j < L) {
           const double v = w[q] * hh;
-          blk[Y::oX + j] = v + a.U[n * (int64_t)L + j];
+          blk[Y::oX + j] = v + uu[q];
         }
       }
     }
@@ -750,17 +764,26 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         }
       }
     }
+    // second (L2-resident) read of dUdt and U instead of 4*Q live registers through the whole solve; again all
+    // loads before the first store
+    double dd[Q], uu[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const int j = lane + 32 * q;
+      dd[q] = (j < L) ? dUg[j] : 0.0;
+      uu[q] = (j < L) ? Ug[j] : 0.0;
+    }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       const int j = lane + 32 * q;
       if (j < L) {
-        double d = dUg[j];  // second (L2-resident) read instead of 2*Q live registers through the whole solve
+        double d = dd[q];
         if (apply) {
           d = d + s[q];
           dUg[j] = d;
         }
         const double inc = d * M::dt;
-        const double un = Ug[j] + inc;
+        const double un = uu[q] + inc;
         Ug[j] = un;
         if (j < nu) blk[Y::oX + j] = un;  // park u = U[0:dim_u] for the epilogue (X is free now)
       }

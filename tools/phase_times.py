@@ -20,7 +20,9 @@ c.step_closed_loop(20)
 c.synchronize()
 t = np.zeros(64, dtype=np.int64)
 check(lib().cgmres_b200_debug_phase_times(c._h, C.c_void_p(t.ctypes.data)))
-names = {1: "alloc+start", 2: "state in, x+dx*h", 3: "first evaluation (3 trajectories, serial lanes)",
+names = {6: "  (state in: global loads -> smem issued)", 7: "  (state in: first barrier)",
+         41: "  (epilogue: back substitution)", 42: "  (epilogue: -)", 43: "  (epilogue: V*y from TMEM + U/dUdt read-modify-write)",
+         1: "alloc+start", 2: "state in, x+dx*h", 3: "first evaluation (3 trajectories, serial lanes)",
          5: "b, r0, ||r0||, v0", 39: "(end of Arnoldi)", 40: "back-subst, V*y, U update, state out"}
 for k in range(5):
     names[10 + 5 * k + 1] = f"k={k}: X = U + h*v"
@@ -31,7 +33,7 @@ for k in range(5):
 for k in range(5):
     if t[50 + 2 * k] and t[51 + 2 * k]:
         print(f"serial warp, k={k}: rollout + costate recursion of 16 lanes = {t[51 + 2 * k] - t[50 + 2 * k]} cycles")
-marks = [i for i in range(50) if t[i] != 0]
+marks = sorted([i for i in range(50) if t[i] != 0], key=lambda i: t[i])
 total = t[marks[-1]] - t[marks[0]]
 prev = marks[0]
 agg = {}
