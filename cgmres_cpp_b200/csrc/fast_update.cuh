@@ -63,6 +63,11 @@ constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved ki
   do {                    \
   } while (0)
 #endif
+// Padding the dim_u rows as well removes the remaining 2-way conflicts of the stage-parallel phase but costs an
+// integer division per element in every element-wise pass: measured slower for msd (4.7e7 vs 5.1e7), so off.
+#ifndef CG_FAST_PAD_U
+#define CG_FAST_PAD_U 0
+#endif
 #ifndef CG_FAST_MAXCTAS
 #define CG_FAST_MAXCTAS 1
 #endif
@@ -78,19 +83,27 @@ struct Lay {
   static constexpr int nx = M::dim_x, nu = M::dim_u, np = M::dim_p, dv = M::dv, km = M::k_max;
   static constexpr int L = nu * dv;
   static constexpr int np1 = np > 0 ? np : 1;
-  static constexpr int XT = nx * (dv > 1 ? dv - 1 : 1);  // stored rollout states xtau[1..dv-1]
-  static constexpr int LTN = nx * dv;                    // stored costates ltau[1..dv]
+  // Shared-memory vectors are stored stage-major with an ODD row stride (SU doubles per stage of dim_u values, SXT
+  // per stage of dim_x values): in the stage-parallel phase lane i works on stage i, and rows 6 or 4 doubles
+  // apart would put 2-4 lanes of a half-warp on the same pair of banks (measured: that phase was bound by the
+  // replayed shared-memory wavefronts of the 16 warps).  Element e = i*dim_u + j of a length-L vector sits at pos(e).
+  static constexpr int SU = CG_FAST_PAD_U ? ((nu % 2 == 0) ? nu + 1 : nu) : nu;
+  static constexpr int SXT = (nx % 2 == 0) ? nx + 1 : nx;
+  static constexpr int LV = dv * SU;                      // doubles of one stored length-L vector
+  static constexpr int XT = SXT * (dv > 1 ? dv - 1 : 1);  // stored rollout states xtau[1..dv-1]
+  static constexpr int LTN = SXT * dv;                    // stored costates ltau[1..dv]
   static constexpr int Q = (L + 31) / 32;                // vector elements per lane
+  static __host__ __device__ constexpr int pos(int e) { return SU == nu ? e : (e / nu) * SU + (e % nu); }
   // per-instance shared-memory block, offsets in doubles.  (U itself is not kept on chip: it is re-read from
   // global memory -- an L2 hit, the CTA touched it microseconds earlier -- where U + h*v is formed and in the
   // final update.)
   static constexpr int oF1 = 0;        // first evaluation: U -> F(U,x+dx*h,t+h) in place; then F_dxh_h (cgmres.hpp:202)
-  static constexpr int oB = oF1 + L;   // first evaluation: U -> F(U,x,t) in place; afterwards the costate plane
-  static constexpr int oX = oB + L;    // first evaluation: U+h*dUdt -> F(..) in place; then U+h*v -> w (cgmres.hpp:168-174)
-  static constexpr int oXT = oX + L;   // rollout states of trajectory A / of the Arnoldi sweeps
+  static constexpr int oB = oF1 + LV;  // first evaluation: U -> F(U,x,t) in place; afterwards the costate plane
+  static constexpr int oX = oB + LV;   // first evaluation: U+h*dUdt -> F(..) in place; then U+h*v -> w (cgmres.hpp:168-174)
+  static constexpr int oXT = oX + LV;  // rollout states of trajectory A / of the Arnoldi sweeps (padded rows)
   static constexpr int oXTB = oXT + XT;   // rollout states of trajectory B (first evaluation only)
   static constexpr int oXTC = oXTB + XT;  // rollout states of trajectory C (first evaluation only)
-  static constexpr bool lt_alias = LTN <= L;  // costates of the Arnoldi sweeps reuse the dead F(U,x,t) area
+  static constexpr bool lt_alias = LTN <= LV;  // costates of the Arnoldi sweeps reuse the dead F(U,x,t) area
   static constexpr int oLT = lt_alias ? oB : oXTC + XT;
   static constexpr int oS = oXTC + XT + (lt_alias ? 0 : LTN);  // scalars
   // scalar slots
@@ -256,7 +269,7 @@ __device__ __forceinline__ void basis_load(uint32_t taddr, double* v) {
 
 // Forward Euler rollout of one instance by ONE lane (cgmres.hpp:132-140): returns xtau[dv] in xc, stores
 // xtau[1..dv-1] to the scratch plane xt.
-template <class M, bool PFULL>
+template <class M, bool PFULL, int SX>
 __device__ __forceinline__ void lane_rollout(const double* __restrict__ in, double* __restrict__ xt,
                                              const double* __restrict__ x0, const double dtau,
                                              const double* __restrict__ pconst, const double* __restrict__ pfull,
@@ -272,7 +285,7 @@ CG_UNROLL(CG_SWEEP_UNROLL)
   for (int i = 0; i < dv; i++) {
     double f[nx];
 #pragma unroll
-    for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+    for (int j = 0; j < nu; j++) u[j] = in[i * Y::SU + j];
     if (PFULL) {
 #pragma unroll
       for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
@@ -285,14 +298,14 @@ CG_UNROLL(CG_SWEEP_UNROLL)
     }
     if (i + 1 < dv) {
 #pragma unroll
-      for (int j = 0; j < nx; j++) xt[i * nx + j] = xc[j];
+      for (int j = 0; j < nx; j++) xt[i * SX + j] = xc[j];
     }
   }
 }
 
 // Full sweep with dHdu inside (used for the three Krylov-independent evaluations, where 3 lanes per instance
 // are busy): out[i] = dHdu(x_i, u_i, p_i, lambda_{i+1})   (cgmres.hpp:113-162)
-template <class M, bool PFULL>
+template <class M, bool PFULL, int SX>
 __device__ __forceinline__ void lane_sweep_full(const double* in, double* out, double* __restrict__ xt,
                                                 const double* __restrict__ x0, const double dtau,
                                                 const double* __restrict__ pconst,
@@ -302,7 +315,7 @@ __device__ __forceinline__ void lane_sweep_full(const double* in, double* out, d
   double xc[nx], lmd[nx], u[nu], p[Y::np1];
 #pragma unroll
   for (int j = 0; j < np; j++) p[j] = pconst[j];
-  lane_rollout<M, PFULL>(in, xt, x0, dtau, pconst, pfull, xc);
+  lane_rollout<M, PFULL, SX>(in, xt, x0, dtau, pconst, pfull, xc);
   if (PFULL) {
 #pragma unroll
     for (int j = 0; j < np; j++) p[j] = pfull[dv * np + j];
@@ -312,16 +325,16 @@ CG_UNROLL(CG_SWEEP_UNROLL)
   for (int i = dv - 1; i >= 0; i--) {  // cgmres.hpp:146-161
     double xi[nx], hu[nu], hx[nx];
 #pragma unroll
-    for (int j = 0; j < nx; j++) xi[j] = (i > 0) ? xt[(i - 1) * nx + j] : x0[j];
+    for (int j = 0; j < nx; j++) xi[j] = (i > 0) ? xt[(i - 1) * SX + j] : x0[j];
 #pragma unroll
-    for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+    for (int j = 0; j < nu; j++) u[j] = in[i * Y::SU + j];
     if (PFULL) {
 #pragma unroll
       for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
     }
     M::dHdu(hu, xi, u, p, lmd);
 #pragma unroll
-    for (int j = 0; j < nu; j++) out[i * nu + j] = hu[j];
+    for (int j = 0; j < nu; j++) out[i * Y::SU + j] = hu[j];
     if (i > 0) {
       M::dHdx(hx, xi, u, p, lmd);
 #pragma unroll
@@ -345,24 +358,25 @@ __device__ __forceinline__ void lane_sweep_costates(const double* __restrict__ i
                                                     const double* __restrict__ pfull) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
+  constexpr int SX = Y::SXT;
   double xc[nx], lmd[nx], u[nu], p[Y::np1];
 #pragma unroll
   for (int j = 0; j < np; j++) p[j] = pconst[j];
-  lane_rollout<M, PFULL>(in, xt, x0, dtau, pconst, pfull, xc);
+  lane_rollout<M, PFULL, SX>(in, xt, x0, dtau, pconst, pfull, xc);
   if (PFULL) {
 #pragma unroll
     for (int j = 0; j < np; j++) p[j] = pfull[dv * np + j];
   }
   M::dPhidx(lmd, xc, p);
 #pragma unroll
-  for (int j = 0; j < nx; j++) lt[(dv - 1) * nx + j] = lmd[j];
+  for (int j = 0; j < nx; j++) lt[(dv - 1) * Y::SXT + j] = lmd[j];
 CG_UNROLL(CG_SWEEP_UNROLL)
   for (int i = dv - 1; i > 0; i--) {
     double xi[nx], hx[nx];
 #pragma unroll
-    for (int j = 0; j < nx; j++) xi[j] = xt[(i - 1) * nx + j];
+    for (int j = 0; j < nx; j++) xi[j] = xt[(i - 1) * SX + j];
 #pragma unroll
-    for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+    for (int j = 0; j < nu; j++) u[j] = in[i * Y::SU + j];
     if (PFULL) {
 #pragma unroll
       for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
@@ -372,7 +386,7 @@ CG_UNROLL(CG_SWEEP_UNROLL)
     for (int j = 0; j < nx; j++) {
       double m = hx[j] * dtau;
       lmd[j] = m + lmd[j];
-      lt[(i - 1) * nx + j] = lmd[j];
+      lt[(i - 1) * Y::SXT + j] = lmd[j];
     }
   }
 }
@@ -435,10 +449,11 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     for (int q = 0; q < Q; q++) {
       const int j = lane + 32 * q;
       if (j < L) {
-        blk[Y::oF1 + j] = uu[q];
-        blk[Y::oB + j] = uu[q];
+        const int e = Y::pos(j);
+        blk[Y::oF1 + e] = uu[q];
+        blk[Y::oB + e] = uu[q];
         double v = dd[q] * hh;  // cgmres.hpp:168-169
-        blk[Y::oX + j] = v + uu[q];
+        blk[Y::oX + e] = v + uu[q];
       }
     }
     if (lane < nx) sc[Y::sX + lane] = a.x[n * nx + lane];
@@ -488,9 +503,11 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     const double* s = b + Y::oS;
     const double* pf = PFULL ? a.ptau + (n0 + g) * (int64_t)((M::dv + 1) * np) : nullptr;
     double* io = b + (tr == 0 ? Y::oF1 : (tr == 1 ? Y::oB : Y::oX));
+    const double* x0p = tr == 1 ? s + Y::sX : s + Y::sXH;
+    const double dtau = tr == 1 ? s[Y::sDT] : s[Y::sDT + 1];
+    // one code path for all three trajectories (lanes of a warp must not diverge here): same padded plane layout
     double* plane = b + (tr == 0 ? Y::oXT : (tr == 1 ? Y::oXTB : Y::oXTC));
-    lane_sweep_full<M, PFULL>(io, io, plane, tr == 1 ? s + Y::sX : s + Y::sXH, tr == 1 ? s[Y::sDT] : s[Y::sDT + 1], s + Y::sP,
-                       pf);
+    lane_sweep_full<M, PFULL, Y::SXT>(io, io, plane, x0p, dtau, s + Y::sP, pf);
   }
   __syncthreads();
 
@@ -505,7 +522,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     for (int q = 0; q < Q; q++) {
       const int j = lane + 32 * q;
       if (j < L) {
-        const double fa = blk[Y::oF1 + j], fb = blk[Y::oB + j], fc = blk[Y::oX + j];
+        const int e = Y::pos(j);
+        const double fa = blk[Y::oF1 + e], fb = blk[Y::oB + e], fc = blk[Y::oX + e];
         double b = fb * c1;  // cgmres.hpp:94-96
         b = b - fa;
         b = b * inv_h;
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         ax = ax * inv_h;
         w[q] = b - ax;  // gmres.hpp:34
         if (EXACT_SUMS)
-          blk[Y::oX + j] = w[q] * w[q];
+          blk[Y::oX + e] = w[q] * w[q];
         else
           ssq += w[q] * w[q];
       }
@@ -526,15 +544,26 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     if (threadIdx.x < n_here) {
       double* b = inst_blk(threadIdx.x);
       double s = 0;
-      constexpr int BS = 10;  // loads of a batch are issued together; the adds keep the reference's order
-      for (int j0 = 0; j0 + BS <= L; j0 += BS) {
-        double v[BS];
+      // loads of a batch are issued together; the adds keep the reference's index order
+      if (Y::SU == nu) {
+        constexpr int BS = 10;
+        for (int j0 = 0; j0 + BS <= L; j0 += BS) {
+          double v[BS];
 #pragma unroll
-        for (int q = 0; q < BS; q++) v[q] = b[Y::oX + j0 + q];
+          for (int q = 0; q < BS; q++) v[q] = b[Y::oX + j0 + q];
 #pragma unroll
-        for (int q = 0; q < BS; q++) s += v[q];
+          for (int q = 0; q < BS; q++) s += v[q];
+        }
+        for (int j = (L / BS) * BS; j < L; j++) s += b[Y::oX + j];
+      } else {
+        for (int i = 0; i < M::dv; i++) {
+          double v[nu];
+#pragma unroll
+          for (int q = 0; q < nu; q++) v[q] = b[Y::oX + i * Y::SU + q];
+#pragma unroll
+          for (int q = 0; q < nu; q++) s += v[q];
+        }
       }
-      for (int j = (L / BS) * BS; j < L; j++) s += b[Y::oX + j];
       b[Y::oS + Y::sRED] = s;
     }
     __syncthreads();
@@ -583,7 +612,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         const int j = lane + 32 * q;
         if (j < L) {
           const double v = w[q] * hh;
-          blk[Y::oX + j] = v + uu[q];
+          blk[Y::oX + Y::pos(j)] = v + uu[q];
         }
       }
     }
@@ -609,25 +638,25 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         double xi[nx], u[nu], p[Y::np1], lm[nx], hu[nu];
 #pragma unroll
         for (int j = 0; j < nx; j++) {
-          xi[j] = (i > 0) ? blk[Y::oXT + (i - 1) * nx + j] : sc[Y::sXH + j];
-          lm[j] = blk[Y::oLT + i * nx + j];
+          xi[j] = (i > 0) ? blk[Y::oXT + (i - 1) * Y::SXT + j] : sc[Y::sXH + j];
+          lm[j] = blk[Y::oLT + i * Y::SXT + j];
         }
 #pragma unroll
-        for (int j = 0; j < nu; j++) u[j] = blk[Y::oX + i * nu + j];
+        for (int j = 0; j < nu; j++) u[j] = blk[Y::oX + i * Y::SU + j];
 #pragma unroll
         for (int j = 0; j < np; j++) p[j] = PFULL ? pf[i * np + j] : sc[Y::sP + j];
         M::dHdu(hu, xi, u, p, lm);
 #pragma unroll
         for (int j = 0; j < nu; j++) {
-          double ax = hu[j] - blk[Y::oF1 + i * nu + j];
-          blk[Y::oX + i * nu + j] = ax * inv_h;
+          double ax = hu[j] - blk[Y::oF1 + i * Y::SU + j];
+          blk[Y::oX + i * Y::SU + j] = ax * inv_h;
         }
       }
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int j = lane + 32 * q;
-        w[q] = (j < L) ? blk[Y::oX + j] : 0.0;
+        w[q] = (j < L) ? blk[Y::oX + Y::pos(j)] : 0.0;
       }
     }
     CG_MARK(10 + 5 * k + 3);
@@ -646,7 +675,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
           const int j = lane + 32 * q;
           if (j < L) {
             if (EXACT_SUMS)
-              blk[Y::oX + j] = c[q] * w[q];
+              blk[Y::oX + Y::pos(j)] = c[q] * w[q];
             else
               part += c[q] * w[q];
           }
@@ -669,7 +698,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         const int j = lane + 32 * q;
         if (j < L) {
           if (EXACT_SUMS)
-            blk[Y::oX + j] = w[q] * w[q];
+            blk[Y::oX + Y::pos(j)] = w[q] * w[q];
           else
             part += w[q] * w[q];
         }
