@@ -631,8 +631,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     __syncthreads();
     CG_MARK(10 + 5 * k + 2);
     if (solving) {
-      // stage-parallel dHdu (cgmres.hpp:156-161) and (F - F1)*inv_h (cgmres.hpp:173-174), one stage per lane;
-      // w_i overwrites u_i in X (same lane reads before it writes): w = A v_k (gmres.hpp:48)
+      // stage-parallel dHdu (cgmres.hpp:156-161), one stage per lane; F_i overwrites u_i in X (same lane reads
+      // before it writes); then w = A v_k = (F - F1)*inv_h (cgmres.hpp:173-174, gmres.hpp:48)
       const double* pf = PFULL ? a.ptau + n * (int64_t)((M::dv + 1) * np) : nullptr;
       for (int i = lane; i < M::dv; i += 32) {
         double xi[nx], u[nu], p[Y::np1], lm[nx], hu[nu];
@@ -647,16 +647,19 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
         for (int j = 0; j < np; j++) p[j] = PFULL ? pf[i * np + j] : sc[Y::sP + j];
         M::dHdu(hu, xi, u, p, lm);
 #pragma unroll
-        for (int j = 0; j < nu; j++) {
-          double ax = hu[j] - blk[Y::oF1 + i * Y::SU + j];
-          blk[Y::oX + i * Y::SU + j] = ax * inv_h;
-        }
+        for (int j = 0; j < nu; j++) blk[Y::oX + i * Y::SU + j] = hu[j];
       }
       __syncwarp();
+      // (F - F1)*inv_h in the element-distributed layout: these shared-memory reads are conflict free, whereas
+      // reading F1 stage-wise above would replay every access (row stride of dim_u doubles)
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int j = lane + 32 * q;
-        w[q] = (j < L) ? blk[Y::oX + Y::pos(j)] : 0.0;
+        w[q] = 0.0;
+        if (j < L) {
+          const double ax = blk[Y::oX + Y::pos(j)] - blk[Y::oF1 + Y::pos(j)];
+          w[q] = ax * inv_h;
+        }
       }
     }
     CG_MARK(10 + 5 * k + 3);
