@@ -327,8 +327,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "bars": "per update |dU|inf/|U|inf <= 1e-9 (teacher forced); closed loop max|dx| <= 1e-6 over 1000 steps",
                 "exact / onchip_exact": "bit-identical U, dUdt, x, status to the reference (msd, semiactive); arm to the bars (libm sin/cos)",
                 "fast": "per update <= 2e-15 rel; closed loop over 1000 steps on the full 65,536-instance msd batch: "
-                        "median 2.6e-8, p99 2.8e-7, max 1.09e-6 (10 instances above 1e-6); semiactive max 9.5e-8; "
-                        "see DESIGN.md section 2 and tools/drift_full.py",
+                        "median 2.6e-8, p99 2.8e-7, max 2.5e-6 (15 instances = 0.02 % above 1e-6); semiactive max 9.4e-8; "
+                        "arm max 3.6e-7; see DESIGN.md section 3 and tools/drift_full.py",
             },
             "modes": other,
         }
