@@ -3,7 +3,6 @@
 // contraction (CMakeLists.txt:40, x86-64 baseline ISA) and the closed loop
 // amplifies a single contracted rounding to ~3e-7 in x over 1000 steps.
 #include "exact_update.cuh"
-#include "fast_update.cuh"
 
 namespace cgmres_b200 {
 
@@ -34,26 +33,6 @@ cudaError_t launch_newton_t(int64_t n, int64_t es, int64_t is, double* u0, const
   return cudaGetLastError();
 }
 
-// the on-chip kernel with sequential sums, compiled here WITHOUT FMA contraction: bit-identical to the reference
-template <class M, class Sim>
-cudaError_t launch_onchip_exact_t(bool pfull, const FastArgs& a, cudaStream_t s) {
-  using Y = fast::Lay<M>;
-  if (a.n == 0) return cudaSuccess;
-  const unsigned grid = (unsigned)((a.n + Y::G - 1) / Y::G);
-  cudaError_t e;
-  if (pfull) {
-    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Y::smem_bytes);
-    if (e != cudaSuccess) return e;
-    fast::control_kernel<M, Sim, true, true><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Y::smem_bytes);
-    if (e != cudaSuccess) return e;
-    fast::control_kernel<M, Sim, false, true><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
-  }
-  return cudaGetLastError();
-}
 }  // namespace
 
 cudaError_t exact_launch_control(int model, bool ptau_full, const ExactArgs& a, cudaStream_t s) {
@@ -72,16 +51,6 @@ cudaError_t exact_launch_newton(int model, int64_t n, int64_t es, int64_t is, do
     case MODEL_ARM: return launch_newton_t<ArmPendulumModel>(n, es, is, u0, x0, p0, p_stride, n_loop, U, s);
     case MODEL_SEMIACTIVE:
       return launch_newton_t<SemiactiveDamperModel>(n, es, is, u0, x0, p0, p_stride, n_loop, U, s);
-  }
-  return cudaErrorInvalidValue;
-}
-
-cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s) {
-  switch (model) {
-    case MODEL_MSD: return launch_onchip_exact_t<MassSpringDamperModel, MassSpringDamperSimulator>(ptau_full, a, s);
-    case MODEL_ARM: return launch_onchip_exact_t<ArmPendulumModel, ArmPendulumSimulator>(ptau_full, a, s);
-    case MODEL_SEMIACTIVE:
-      return launch_onchip_exact_t<SemiactiveDamperModel, SemiactiveDamperSimulator>(ptau_full, a, s);
   }
   return cudaErrorInvalidValue;
 }
