@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
 
   // ---- tensor memory: one allocation, released at the end by the same warp --------------------------------------
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)G * Y::stride);
+  CG_MARK_SERIAL(60);
   if (wid == 0) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tmem_slot);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst),
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, Lay<M>::ctas_per_sm) control_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  CG_MARK_SERIAL(61);
 
   CG_MARK(1);
   // ---- phase 0: state in.  F1 and B areas <- U, X <- U + h*dUdt (third trajectory), x, p(t) -----------------

@@ -33,6 +33,8 @@ for k in range(5):
 for k in range(5):
     if t[50 + 2 * k] and t[51 + 2 * k]:
         print(f"serial warp, k={k}: rollout + costate recursion of 16 lanes = {t[51 + 2 * k] - t[50 + 2 * k]} cycles")
+if t[60] and t[61]:
+    print(f"warp 0: tcgen05.alloc + relinquish = {t[61] - t[60]} cycles; CTA start to first mark of warp 5 = {t[1] - t[60]} cycles")
 marks = sorted([i for i in range(50) if t[i] != 0], key=lambda i: t[i])
 total = t[marks[-1]] - t[marks[0]]
 prev = marks[0]
