@@ -157,7 +157,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
 
     import cgmres_cpp_b200 as cg
-    from oracle import pyoracle as po  # only for the seeded synthetic inputs and the cpu_baseline leg
+    from cgmres_cpp_b200 import workloads  # seeded synthetic inputs (oracle/ is only touched by the CPU-baseline leg)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference)")
@@ -178,7 +178,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     from cgmres_cpp_b200.sharding import aggregate_updates_per_second, max_over_ranks, weak_scaling_range
 
     lo, hi = weak_scaling_range(n, world, rank)
-    x0_all, p_all, u0 = po.synthetic_batch(model_id, n * world, seed=12345)
+    x0_all, p_all, u0 = workloads.synthetic_batch(model_id, n * world, seed=12345)
     x0, p = x0_all[lo:hi], p_all[lo:hi]
 
     ctl = cg.BatchedCgmres(model_id, n, device=local_rank, mode=mode)

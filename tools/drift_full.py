@@ -5,7 +5,7 @@ import argparse, os, sys, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cgmres_cpp_b200 as cg
-from oracle import pyoracle as po
+from cgmres_cpp_b200 import workloads as po
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="msd")

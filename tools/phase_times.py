@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cgmres_cpp_b200 as cg  # noqa: E402
 from cgmres_cpp_b200._lib import check, lib  # noqa: E402
-from oracle import pyoracle as po  # noqa: E402
+from cgmres_cpp_b200 import workloads as po  # noqa: E402
 
 model = {"msd": 0, "arm": 1, "semiactive": 2}[sys.argv[1] if len(sys.argv) > 1 else "msd"]
 n = 65536

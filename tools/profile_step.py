@@ -6,7 +6,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cgmres_cpp_b200 as cg  # noqa: E402
-from oracle import pyoracle as po  # noqa: E402  (seeded synthetic inputs only)
+from cgmres_cpp_b200 import workloads as po  # noqa: E402  (seeded synthetic inputs)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="msd", choices=("msd", "arm", "semiactive"))
