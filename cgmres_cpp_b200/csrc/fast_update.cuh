@@ -37,9 +37,9 @@ namespace cgmres_b200 {
 namespace fast {
 
 constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved kilobyte
-// max instances (= warps) per CTA.  Register file: 16 warps leave 128 registers per thread, 20 warps 102; the
-// kernels with long vector slices (Q >= 8 per lane) or a 4-state sweep need ~110-125, semiactive ~95 (GPU sweep in
-// profiles/README.md: msd 16 > 18/20 (spills) > 12; semiactive 20 > 16).
+// max instances (= warps) per CTA.  Register file: 16 warps leave 128 registers per thread, 24 warps 85; the
+// kernels with long vector slices (Q >= 8 per lane) or a 4-state sweep need ~110-125, semiactive 80 (GPU sweep in
+// profiles/README.md: msd 16 > 18/20 > 12; semiactive 28 (spills) > 24 > 20 > 16).
 #ifndef CG_SWEEP_UNROLL
 #define CG_SWEEP_UNROLL 5  // stages per unrolled body of the serial recursions (exposes the next stages' loads)
 #endif
@@ -75,7 +75,7 @@ constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved ki
 #define CG_FAST_GCAP(Q, NX) (CG_FAST_GFORCE)
 #endif
 #ifndef CG_FAST_GCAP
-#define CG_FAST_GCAP(Q, NX) (((Q) >= 8 || (NX) > 2) ? 16 : 20)
+#define CG_FAST_GCAP(Q, NX) (((Q) >= 8 || (NX) > 2) ? 16 : 24)
 #endif
 
 template <class M>
