@@ -84,6 +84,8 @@ struct cgmres_b200_controller {
   int32_t* status = nullptr;
   double* t_inst = nullptr;  // per-instance controller clocks (set_t); null = lock step with `t`
   long long* dbg = nullptr;  // 64 phase timestamps of one warp (debug builds of the on-chip kernel)
+  double* scratch = nullptr;       // fast mode: spill regions of the pipelined kernel, one per concurrent launch
+  size_t scratch_region = 0;       // doubles per region
   double* stage = nullptr;  // instance-major staging, grown on demand
   size_t stage_doubles = 0;
 
@@ -124,6 +126,10 @@ struct cgmres_b200_controller {
       if ((rc = dalloc(&u_out, l * mi->dim_u))) return rc;
       if ((rc = dalloc(&status, l))) return rc;
       if ((rc = dalloc(&dbg, 64))) return rc;
+      if (mode == CGMRES_B200_MODE_FAST) {  // region 0: full-batch launches; 1..kSlices: the pipelined slices
+        scratch_region = fast_scratch_doubles(model, device);
+        if (scratch_region && (rc = dalloc(&scratch, scratch_region * (size_t)(kSlices + 1)))) return rc;
+      }
       if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;
       return 0;
     }
@@ -152,6 +158,7 @@ struct cgmres_b200_controller {
     cudaFree(status);
     cudaFree(t_inst);
     cudaFree(dbg);
+    cudaFree(scratch);
     cudaFree(stage);
     for (int i = 0; i < kSlices; i++) {
       if (side[i]) cudaStreamDestroy(side[i]);
@@ -172,7 +179,7 @@ struct cgmres_b200_controller {
   }
 
   // on-chip modes: one update of instances [lo, lo+cnt) on stream s (pointer offsets into the instance-major state)
-  int launch_slice(int64_t lo, int64_t cnt, int plant, double dt_t, double dt_th, cudaStream_t s) {
+  int launch_slice(int64_t lo, int64_t cnt, int plant, double dt_t, double dt_th, cudaStream_t s, int region = 0) {
     FastArgs f;
     const int64_t prow = ptau_full ? (int64_t)ptau_rows_full() : (int64_t)mi->dim_p;
     f.n = cnt;
@@ -187,6 +194,7 @@ struct cgmres_b200_controller {
     f.t_inst = t_inst ? t_inst + lo : nullptr;
     f.plant = plant;
     f.dbg = dbg;
+    f.scratch = scratch ? scratch + scratch_region * (size_t)region : nullptr;
     if (mode == CGMRES_B200_MODE_FAST)
       CU(fast_launch_control(model, ptau_full, f, s));
     else
@@ -503,7 +511,7 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
       cudaStream_t st = h->side[i];
       CU(cudaStreamWaitEvent(st, h->ev_begin, 0));
       CU(cudaMemcpyAsync(h->x + lo * nx, x + lo * nx, sizeof(double) * (size_t)cnt * nx, cudaMemcpyHostToDevice, st));
-      int rcu = h->launch_slice(lo, cnt, 0, dt_t, dt_th, st);
+      int rcu = h->launch_slice(lo, cnt, 0, dt_t, dt_th, st, 1 + i);
       if (rcu) return rcu;
       CU(cudaMemcpyAsync(u + lo * nu, h->u_out + lo * nu, sizeof(double) * (size_t)cnt * nu, cudaMemcpyDeviceToHost,
                          st));

@@ -1,14 +1,71 @@
 // fast_kernels.cu -- instantiations of the on-chip control-update kernel with FMA contraction and shuffle
 // reductions (default nvcc floating-point flags; NOT -fmad=false).
+// The serial recursions are unrolled 10 stages deep in this translation unit (5 in the verification twin): in
+// the pipelined kernel the serial warp competes with 16 busy vector warps for the shared-memory pipeline, and
+// exposing the loads of 10 stages at once hides that latency better (GPU sweep: 2 -> 5.3e7, 5 -> 6.1e7,
+// 10 -> 6.3e7, 25 -> 6.0e7 with spills).
+#ifndef CG_SWEEP_UNROLL
+#define CG_SWEEP_UNROLL 10
+#endif
 #include "fast_update.cuh"
+#include "pipe_update.cuh"
 
 // experiment knob (tools/sweep_build.sh): build the "fast" entry point with the reference's sequential sums
 #ifndef CG_FAST_SEQ_SUMS
 #define CG_FAST_SEQ_SUMS false
 #endif
 
+// 1: the persistent warp-specialised kernel (pipe_update.cuh) serves the fast mode; 0: the first-generation
+// one-round-per-CTA kernel (fast_update.cuh).  Per model: the pipelined kernel wins where the vector work and the
+// serial recursion are of similar length (msd, semiactive).
+#ifndef CG_FAST_PIPE_MSD
+#define CG_FAST_PIPE_MSD 1
+#endif
+#ifndef CG_FAST_PIPE_ARM
+#define CG_FAST_PIPE_ARM 1
+#endif
+#ifndef CG_FAST_PIPE_SEMI
+#define CG_FAST_PIPE_SEMI 1
+#endif
+
 namespace cgmres_b200 {
 namespace {
+int sm_count(int device) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) device = 0;
+  if (cached[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+    cached[device] = v;
+  }
+  return cached[device];
+}
+
+template <class M, class Sim>
+cudaError_t launch_pipe(bool pfull, const FastArgs& a, cudaStream_t s) {
+  using Y = pipe::Lay<M>;
+  if (a.n == 0) return cudaSuccess;
+  if (a.scratch == nullptr) return cudaErrorInvalidValue;
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e != cudaSuccess) return e;
+  const int64_t rounds = (a.n + Y::NI - 1) / Y::NI;
+  const int sms = sm_count(device);
+  const unsigned grid = (unsigned)(rounds < (int64_t)sms ? rounds : (int64_t)sms);  // persistent: one CTA per SM
+  if (pfull) {
+    e = cudaFuncSetAttribute(pipe::control_kernel<M, Sim, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Y::smem_bytes);
+    if (e != cudaSuccess) return e;
+    pipe::control_kernel<M, Sim, true><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(pipe::control_kernel<M, Sim, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Y::smem_bytes);
+    if (e != cudaSuccess) return e;
+    pipe::control_kernel<M, Sim, false><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
 template <class M, class Sim>
 cudaError_t launch_t(bool pfull, const FastArgs& a, cudaStream_t s) {
   using Y = fast::Lay<M>;
@@ -32,18 +89,36 @@ cudaError_t launch_t(bool pfull, const FastArgs& a, cudaStream_t s) {
 
 cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s) {
   switch (model) {
-    case MODEL_MSD: return launch_t<MassSpringDamperModel, MassSpringDamperSimulator>(ptau_full, a, s);
-    case MODEL_ARM: return launch_t<ArmPendulumModel, ArmPendulumSimulator>(ptau_full, a, s);
-    case MODEL_SEMIACTIVE: return launch_t<SemiactiveDamperModel, SemiactiveDamperSimulator>(ptau_full, a, s);
+    case MODEL_MSD:
+      return CG_FAST_PIPE_MSD ? launch_pipe<MassSpringDamperModel, MassSpringDamperSimulator>(ptau_full, a, s)
+                              : launch_t<MassSpringDamperModel, MassSpringDamperSimulator>(ptau_full, a, s);
+    case MODEL_ARM:
+      return CG_FAST_PIPE_ARM ? launch_pipe<ArmPendulumModel, ArmPendulumSimulator>(ptau_full, a, s)
+                              : launch_t<ArmPendulumModel, ArmPendulumSimulator>(ptau_full, a, s);
+    case MODEL_SEMIACTIVE:
+      return CG_FAST_PIPE_SEMI ? launch_pipe<SemiactiveDamperModel, SemiactiveDamperSimulator>(ptau_full, a, s)
+                               : launch_t<SemiactiveDamperModel, SemiactiveDamperSimulator>(ptau_full, a, s);
   }
   return cudaErrorInvalidValue;
 }
 
+size_t fast_scratch_doubles(int model, int device) {
+  const size_t ctas = (size_t)sm_count(device);
+  switch (model) {
+    case MODEL_MSD: return CG_FAST_PIPE_MSD ? ctas * pipe::Lay<MassSpringDamperModel>::scratch_doubles_per_cta : 0;
+    case MODEL_ARM: return CG_FAST_PIPE_ARM ? ctas * pipe::Lay<ArmPendulumModel>::scratch_doubles_per_cta : 0;
+    case MODEL_SEMIACTIVE:
+      return CG_FAST_PIPE_SEMI ? ctas * pipe::Lay<SemiactiveDamperModel>::scratch_doubles_per_cta : 0;
+  }
+  return 0;
+}
+
 int fast_instances_per_cta(int model) {
   switch (model) {
-    case MODEL_MSD: return fast::Lay<MassSpringDamperModel>::G;
-    case MODEL_ARM: return fast::Lay<ArmPendulumModel>::G;
-    case MODEL_SEMIACTIVE: return fast::Lay<SemiactiveDamperModel>::G;
+    case MODEL_MSD: return CG_FAST_PIPE_MSD ? pipe::Lay<MassSpringDamperModel>::NI : fast::Lay<MassSpringDamperModel>::G;
+    case MODEL_ARM: return CG_FAST_PIPE_ARM ? pipe::Lay<ArmPendulumModel>::NI : fast::Lay<ArmPendulumModel>::G;
+    case MODEL_SEMIACTIVE:
+      return CG_FAST_PIPE_SEMI ? pipe::Lay<SemiactiveDamperModel>::NI : fast::Lay<SemiactiveDamperModel>::G;
   }
   return 0;
 }

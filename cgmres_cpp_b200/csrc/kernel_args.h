@@ -54,6 +54,8 @@ struct FastArgs {
   double* t_inst;      // null: lock step (dtau from the host); else per-instance clocks [n], dtau evaluated on device
   int plant;
   long long* dbg;      // phase timestamps (debug builds with -DCG_FAST_TIMING), else unused / null
+  double* scratch;     // pipelined fast kernel: per-CTA spill area (fast_scratch_doubles()), one region per
+                       // concurrently running launch; unused by the other on-chip kernels
 };
 
 // on-chip kernels: fast_kernels.cu (FMA, shuffle reductions) and their sequential-sum, no-FMA twin compiled in
@@ -61,6 +63,8 @@ struct FastArgs {
 cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 int fast_instances_per_cta(int model);
+// doubles of global scratch one launch of the fast kernel needs on `device` (0: none)
+size_t fast_scratch_doubles(int model, int device);
 
 // exact mode (exact_kernels.cu)
 cudaError_t exact_launch_control(int model, bool ptau_full, const ExactArgs& a, cudaStream_t s);

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Blocked-vs-total cycles per warp of CTA 0 of the pipelined fast kernel (library built with
+FAST_EXTRA=-DCG_PIPE_TIMING): warp 0 is the serial warp, the others are vector warps."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cgmres_cpp_b200 as cg  # noqa: E402
+from cgmres_cpp_b200._lib import check, lib  # noqa: E402
+from cgmres_cpp_b200 import workloads as po  # noqa: E402
+
+model = {"msd": 0, "arm": 1, "semiactive": 2}[sys.argv[1] if len(sys.argv) > 1 else "msd"]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+x0, p, u0 = po.synthetic_batch(model, n)
+c = cg.BatchedCgmres(model, n, mode=cg.MODE_FAST)
+if p is not None:
+    c.set_ptau_repeat(p)
+c.init_u0(u0); c.init_u0_newton(u0, x0, p, 10); c.set_x(x0)
+c.step_closed_loop(20)
+c.synchronize()
+t = np.zeros(64, dtype=np.int64)
+check(lib().cgmres_b200_debug_phase_times(c._h, C.c_void_p(t.ctypes.data)))
+per = cg.instances_per_cta(model) if hasattr(cg, "instances_per_cta") else 0
+for w in range(24):
+    if t[2 * w + 1]:
+        role = "serial" if w == 0 else "vector"
+        print(f"warp {w:2d} ({role}): total {t[2*w+1]:8d} cycles, blocked at barriers {t[2*w]:8d} = {100.0*t[2*w]/t[2*w+1]:.1f} %")

@@ -1,12 +1,13 @@
 #!/bin/bash
-# usage: tools/sweep_fast.sh "<extra nvcc flags for fast_kernels.cu>"   (GPU box: rebuild, msd bench + full-size drift)
-flags="$1"
+# usage: tools/sweep_fast.sh "<nvcc -D flags for fast_kernels.cu>" [bench args...]
+# (run on the GPU box: rebuild only the fast-mode translation unit with the flags, then a short bench)
+flags="$1"; shift
 touch cgmres_cpp_b200/csrc/fast_kernels.cu
-make -C cgmres_cpp_b200/csrc FAST_EXTRA="$flags" > /dev/null 2>&1 || { echo "build failed: $flags"; exit 1; }
-python bench.py --steps 40 --warmup 4 --no-cpu-baseline --no-other-modes --mode fast 2>&1 | tail -1 > /tmp/sweep_line.json
-python tools/drift_full.py --model msd > /tmp/drift.json
-python - "$flags" <<'PY'
+make -j8 -C cgmres_cpp_b200/csrc FAST_EXTRA="$flags" > /dev/null 2>&1 || { echo "build failed: $flags"; exit 1; }
+spill=$(grep -o "[0-9]* bytes spill stores" cgmres_cpp_b200/_build/fast_kernels.ptxas.log | sort -n | tail -1 | tr -d '\n')
+timeout 300 python bench.py --steps 40 --warmup 4 --no-cpu-baseline --no-other-modes "$@" 2>&1 | tail -1 > /tmp/sweep_line.json
+python - "$flags" "$spill" <<'PY'
 import json, sys
-d = json.loads(open('/tmp/sweep_line.json').read()); r = json.loads(open('/tmp/drift.json').read())
-print('%-40s ms/step %.3f value %.3e | drift max %.3e p99 %.3e n>1e-6 %d' % (sys.argv[1] or '(default)', d['ms_per_step'], d['value'], r['max_abs_dx'], r['p99_abs_dx'], r['n_above_1e-6']))
+d = json.loads(open('/tmp/sweep_line.json').read())
+print('%-44s max %-24s value %.4e  ms/step %.3f' % (sys.argv[1], sys.argv[2], d['value'], d['ms_per_step']))
 PY
