@@ -127,7 +127,7 @@ struct cgmres_b200_controller {
       if ((rc = dalloc(&status, l))) return rc;
       if ((rc = dalloc(&dbg, 64))) return rc;
       if (mode == CGMRES_B200_MODE_FAST) {  // region 0: full-batch launches; 1..kSlices: the pipelined slices
-        scratch_region = fast_scratch_doubles(model, device);
+        scratch_region = fast_scratch_doubles(model, device, n);
         if (scratch_region && (rc = dalloc(&scratch, scratch_region * (size_t)(kSlices + 1)))) return rc;
       }
       if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;

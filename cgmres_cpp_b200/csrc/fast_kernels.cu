@@ -102,13 +102,21 @@ cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cu
   return cudaErrorInvalidValue;
 }
 
-size_t fast_scratch_doubles(int model, int device) {
-  const size_t ctas = (size_t)sm_count(device);
+namespace {
+template <class M>
+size_t scratch_for(int device, int64_t n) {
+  using Y = pipe::Lay<M>;
+  const int64_t rounds = (n + Y::NI - 1) / Y::NI;
+  const int64_t ctas = rounds < (int64_t)sm_count(device) ? rounds : (int64_t)sm_count(device);
+  return (size_t)(ctas > 0 ? ctas : 1) * Y::scratch_doubles_per_cta;
+}
+}  // namespace
+
+size_t fast_scratch_doubles(int model, int device, int64_t n) {
   switch (model) {
-    case MODEL_MSD: return CG_FAST_PIPE_MSD ? ctas * pipe::Lay<MassSpringDamperModel>::scratch_doubles_per_cta : 0;
-    case MODEL_ARM: return CG_FAST_PIPE_ARM ? ctas * pipe::Lay<ArmPendulumModel>::scratch_doubles_per_cta : 0;
-    case MODEL_SEMIACTIVE:
-      return CG_FAST_PIPE_SEMI ? ctas * pipe::Lay<SemiactiveDamperModel>::scratch_doubles_per_cta : 0;
+    case MODEL_MSD: return CG_FAST_PIPE_MSD ? scratch_for<MassSpringDamperModel>(device, n) : 0;
+    case MODEL_ARM: return CG_FAST_PIPE_ARM ? scratch_for<ArmPendulumModel>(device, n) : 0;
+    case MODEL_SEMIACTIVE: return CG_FAST_PIPE_SEMI ? scratch_for<SemiactiveDamperModel>(device, n) : 0;
   }
   return 0;
 }

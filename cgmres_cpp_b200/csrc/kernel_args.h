@@ -63,8 +63,8 @@ struct FastArgs {
 cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 int fast_instances_per_cta(int model);
-// doubles of global scratch one launch of the fast kernel needs on `device` (0: none)
-size_t fast_scratch_doubles(int model, int device);
+// doubles of global scratch one launch of the fast kernel over (up to) n instances needs on `device` (0: none)
+size_t fast_scratch_doubles(int model, int device, int64_t n);
 
 // exact mode (exact_kernels.cu)
 cudaError_t exact_launch_control(int model, bool ptau_full, const ExactArgs& a, cudaStream_t s);

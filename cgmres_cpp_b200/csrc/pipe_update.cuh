@@ -7,18 +7,26 @@
 // during which the 16 vector warps of the CTA idle at a barrier, and during the vector phases the serial warp
 // idles.  Here
 //   * ONE CTA per SM holds NG = 2 groups of GI = 16 instances (32 resident instances per SM instead of 16);
-//   * warps 0..GI-1 are VECTOR warps: warp w owns instance w of group 0 AND instance w of group 1 and alternates
-//     between them (dHdu per stage, (F - F1)/h, Gram-Schmidt with shuffle reductions, Householder scalars,
-//     U + h*v for the next sweep, final update);
-//   * warp GI is the SERIAL warp: lane l runs the transposed recursion of instance l of the group whose inputs are
-//     ready (two lanes per instance for the fused F(U,x+dx*h,t+h) / F(U,x,t) pair of the first evaluation);
-//   * the two roles hand groups to each other through named barriers (bar.arrive by the producer, bar.sync by the
-//     consumer): while the serial warp sweeps group A the vector warps work on group B and vice versa, in steady
-//     state across rounds as well (the kernel is persistent: CTA b processes rounds b, b + gridDim.x, ...).
+//   * VECTOR warp v owns instance v of group 0 AND instance v of group 1 and alternates between them (dHdu per
+//     stage, (F - F1)/h, Gram-Schmidt with shuffle reductions, Householder scalars, U + h*v for the next sweep,
+//     final update);
+//   * each group has its own SERIAL warp: lane l runs the transposed recursion of instance l of that group (two
+//     lanes per instance for the fused F(U,x+dx*h,t+h) / F(U,x,t) pair of the first evaluation);
+//   * the roles hand a group to each other through named barriers (bar.arrive by the producer, bar.sync by the
+//     consumer): while group A is being swept by its serial warp the vector warps work on group B and vice versa,
+//     in steady state across rounds as well (the kernel is persistent: CTA b processes rounds b, b + gridDim.x, ..
+//     and a round's final update is deferred into the next round's first step, where the vector warps would
+//     otherwise wait for the first sweep);
+//   * warp placement matters: the serial warps are warps 0 and 4, i.e. they have scheduler 0 (warp id % 4) almost
+//     to themselves, because their dependent chains must not queue for issue slots behind the bursty vector
+//     warps (measured: 5.3e7 -> 6.0e7 updates/s from the placement alone); the vector warps are the warps whose id
+//     is not a multiple of 4 (schedulers and TMEM lane quarters 1..3, five warps each = 96 registers per thread),
+//     the 16th is warp 8.
 // Doubling the residency needs the per-instance shared-memory block to shrink from 13.4 KB to 6.8 KB (msd):
-// F(U,x+dx*h,t+h) ("F1", cgmres.hpp:202) moves into tensor memory next to the first Krylov vectors; what does not
-// fit in the 256 KB of TMEM (v_2..v_4 for msd; nothing for the smaller models) and the transient F(U,x,t) go to a
-// per-CTA global scratch that is reused every round and therefore stays in L2 (148 x 300 KB << 126 MB).
+// F(U,x+dx*h,t+h) ("F1", cgmres.hpp:202) moves into tensor memory next to the first Krylov vector; what does not
+// fit in the TMEM quarters the vector warps can reach (v_1..v_4 for msd; nothing for the smaller models) and the
+// transient F(U,x,t) go to a per-CTA global scratch that is reused every round and therefore stays in L2
+// (148 x 384 KB << 126 MB; the L2 still writes about half of those stores back to HBM).
 //
 // Arithmetic is the same as fast_update.cuh's FAST instantiation (FMA contraction, butterfly sums): results are
 // identical to that kernel, tolerance parity against the reference.
@@ -42,12 +50,9 @@ struct Lay {
   static constexpr int NVEC = km + 1;  // stored vectors per instance: id 0 = F1, id 1+i = v_i
   // tensor memory: 2*Q columns per vector; warps w, w+4, ... share a lane quarter
   static constexpr int tcols_vec = 2 * Q;
-  // warp roles: the serial warp is warp 0 and has scheduler 0 (warp id % 4) to itself -- its dependent chain is
-  // the critical path and must not queue for issue slots behind the bursty vector warps; vector warp v is warp
-  // 1 + v + v/3 (ids that are not multiples of 4, i.e. schedulers and TMEM lane quarters 1..3); the other
-  // multiples of 4 below NW exit at once.
-  // (A 16th vector warp would be the sixth on one scheduler and cap the kernel at 80 registers; it shares
-  //  scheduler 0 with the serial warp instead, as warp 4.)
+  // warp roles (see the header comment): serial warps 0, 4; vector warp v < 15 is warp 1 + v + v/3; further vector
+  // warps are warps 8, 12, ..; other multiples of 4 below NW idle.  (A 16th vector warp on schedulers 1..3 would be
+  // the sixth on one of them and cap the kernel at 80 registers.)
   static constexpr int GV3 = GI < 15 ? GI : 15;  // vector warps on schedulers 1..3
   static constexpr int last_vec_wid = 1 + (GV3 - 1) + (GV3 - 1) / 3;
   static constexpr int last_s0_wid = 4 * (NG - 1 + GI - GV3);  // serial warps 0, 4; vector warps GV3.. are 8, ...
@@ -114,6 +119,22 @@ __device__ __forceinline__ void bar_sync(int id, int count) {
 __device__ __forceinline__ void bar_arrive(int id, int count) {
   __threadfence_block();  // the producer's shared/global stores are visible before the consumer is released
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// scratch accesses carry an L2 evict-last policy: the per-CTA scratch is rewritten every round and must not be
+// pushed out (and written back to HBM) by the U / dUdt lines streaming through the L2
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_keep(double* p, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double ld_keep(const double* p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
 }
 
 template <class M, class Sim, bool PFULL>
@@ -213,6 +234,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
     }
   } else if (vw >= 0) {
     // =============================== vector warps: warp = instance (of each group) ==============================
+    const uint64_t keep = l2_evict_last_policy();
     const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (wid & 3)) << 16) + (uint32_t)((wid >> 2) * Y::tcols_warp);
 
     // stored vectors: id 0 = F1, 1+i = v_i; the first NVT live in this warp's TMEM slot of the group, the rest in
@@ -224,7 +246,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
 #pragma unroll
         for (int q = 0; q < Q; q++) {
           const int j = lane + 32 * q;
-          if (j < L) scr[(size_t)(id - Y::NVT) * L + j] = v[q];
+          if (j < L) st_keep(scr + (size_t)(id - Y::NVT) * L + j, v[q], keep);
         }
       }
     };
@@ -235,7 +257,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
 #pragma unroll
         for (int q = 0; q < Q; q++) {
           const int j = lane + 32 * q;
-          v[q] = (j < L) ? scr[(size_t)(id - Y::NVT) * L + j] : 0.0;
+          v[q] = (j < L) ? ld_keep(scr + (size_t)(id - Y::NVT) * L + j, keep) : 0.0;
         }
       }
     };
@@ -328,8 +350,10 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int j = lane + 32 * q;
-        dd[q] = (j < L) ? dUg[j] : 0.0;
-        uu[q] = (j < L) ? Ug[j] : 0.0;
+        // last touch of this instance's U / dUdt in this launch: evict-first loads and stores, so that the L2
+        // keeps the CTAs' scratch vectors (re-used every round) instead of these dead lines
+        dd[q] = (j < L) ? __ldcs(dUg + j) : 0.0;
+        uu[q] = (j < L) ? __ldcs(Ug + j) : 0.0;
       }
       double un0 = 0.0;  // element `lane` of the new U: lanes 0..dim_u-1 hold u = U[0:dim_u]
 #pragma unroll
@@ -339,11 +363,11 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           double d = dd[q];
           if (apply) {
             d = d + s[q];
-            dUg[j] = d;
+            __stcs(dUg + j, d);
           }
           const double inc = d * M::dt;
           const double un = uu[q] + inc;
-          Ug[j] = un;
+          __stcs(Ug + j, un);
           if (q == 0) un0 = un;
         }
       }
