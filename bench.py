@@ -309,7 +309,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "p50_per_update_latency_us": p50_ms * 1e3 / n,
             "roofline": {
                 "bound": "fp64", "achieved": flops, "peak": peak_fma, "unit": "TFLOP/s", "frac": flops / peak_fma,
-                "traffic": traffic, "kernel": "%s::control_kernel (one launch = one control update + plant step per instance)" % ("exact" if args.mode == "exact" else "fast"),
+                "traffic": traffic, "kernel": "%s::control_kernel (one launch = one control update + plant step per instance)" % {"exact": "exact", "onchip_exact": "fast", "fast": "pipe"}.get(args.mode, args.mode),
                 "flop_per_update": FLOP_PER_UPDATE[model], "launch_ms": launch_ms,
                 "peak_source": "measured live: 8 DFMA chains/thread microbenchmark (cgmres_b200_measure_fp64_peak)",
                 "peak_no_fma": peak_nofma, "frac_of_no_fma_peak": flops / peak_nofma,

@@ -105,7 +105,15 @@ struct Lay {
     if (*(volatile double*)sm == 1.2345e300) (acc) += 1;        \
     (acc) += clock64() - t_wait0_;                              \
   } while (0)
+#define CG_PIPE_WORK_BEGIN const long long t_work0_ = clock64()
+#define CG_PIPE_WORK_END(acc) (acc) += clock64() - t_work0_
 #else
+#define CG_PIPE_WORK_BEGIN \
+  do {                     \
+  } while (0)
+#define CG_PIPE_WORK_END(acc) \
+  do {                        \
+  } while (0)
 #define CG_PIPE_WAIT_BEGIN \
   do {                     \
   } while (0)
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   auto BL = [](int g) { return 1 + NG + g; };
   double* const scr_cta = a.scratch + (size_t)blockIdx.x * Y::scratch_doubles_per_cta;
 #ifdef CG_PIPE_TIMING
-  long long t_wait = 0;
+  long long t_wait = 0, t_p1 = 0, t_p2 = 0, t_sw = 0;
   const long long t_begin = clock64();
 #endif
 
@@ -195,7 +203,9 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           const double* x0p = tr == 0 ? s + Y::sXH : s + Y::sX;
           const double dtau = tr == 0 ? s[Y::sDT + 1] : s[Y::sDT];
           double* plane = b + (tr == 0 ? Y::oXT : Y::oLT);
+          CG_PIPE_WORK_BEGIN;
           fast::lane_sweep_full<M, PFULL, Y::SXT>(b + Y::oX, out, plane, x0p, dtau, s + Y::sP, pf);
+          CG_PIPE_WORK_END(t_p1);
         }
         bar_arrive(BL(g), T);
       }
@@ -208,8 +218,10 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           double* b = sm + (size_t)(g * GI + lane) * Y::stride;
           const double* s = b + Y::oS;
           const double* pf = PFULL ? a.ptau + (n0 + lane) * prow : nullptr;
+          CG_PIPE_WORK_BEGIN;
           fast::lane_sweep_costates<M, PFULL>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, s[Y::sDT + 1],
                                               s + Y::sP, pf);
+          CG_PIPE_WORK_END(t_p2);
         }
         bar_arrive(BL(g), T);
       }
@@ -224,8 +236,10 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
             const double* s = b + Y::oS;
             if (s[Y::sFLAG] == 0.0) {
               const double* pf = PFULL ? a.ptau + (n0 + lane) * prow : nullptr;
+              CG_PIPE_WORK_BEGIN;
               fast::lane_sweep_costates<M, PFULL>(b + Y::oX, b + Y::oXT, b + Y::oLT, s + Y::sXH, s[Y::sDT + 1],
                                                   s + Y::sP, pf);
+              CG_PIPE_WORK_END(t_sw);
             }
           }
           bar_arrive(BL(g), T);
@@ -667,6 +681,11 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   if (a.dbg && blockIdx.x == 0 && lane == 0 && wid < 24) {  // [2*wid] = cycles blocked, [2*wid+1] = total
     a.dbg[2 * wid] = t_wait;
     a.dbg[2 * wid + 1] = clock64() - t_begin;
+    if (wid == 0) {  // serial warp of group 0: cycles inside the first pass, the second pass, the Arnoldi sweeps
+      a.dbg[48] = t_p1;
+      a.dbg[49] = t_p2;
+      a.dbg[50] = t_sw;
+    }
   }
 #endif
   // ---- release tensor memory ------------------------------------------------------------------------------------

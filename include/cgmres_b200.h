@@ -44,10 +44,11 @@ enum {
 /* build modes */
 enum {
   CGMRES_B200_MODE_EXACT = 0, /* reference operation order, no FMA: bit-identical U and x (no-libm models) */
-  CGMRES_B200_MODE_FAST = 1,  /* on-chip kernel (one CTA per instance group, state in shared memory/registers),
-                                 FMA + shuffle reductions: within the north-star tolerances                */
-  CGMRES_B200_MODE_ONCHIP_EXACT = 2 /* the same on-chip kernel with the reference's sequential sums and no FMA:
-                                 bit-identical like MODE_EXACT (verification build of the fast kernel)      */
+  CGMRES_B200_MODE_FAST = 1,  /* persistent on-chip kernel (instance groups resident in shared / tensor memory,
+                                 serial-recursion and vector warps pipelined), FMA + shuffle reductions: within
+                                 the north-star tolerances                                                  */
+  CGMRES_B200_MODE_ONCHIP_EXACT = 2 /* on-chip kernel (one CTA per instance group) with the reference's sequential
+                                 sums and no FMA: bit-identical like MODE_EXACT                             */
 };
 
 /* status word of an instance's last update: exit code in bits 0..7, Krylov columns used in bits 8..15 */

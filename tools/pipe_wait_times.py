@@ -28,3 +28,5 @@ for w in range(24):
     if t[2 * w + 1]:
         role = "serial" if w == 0 else "vector"
         print(f"warp {w:2d} ({role}): total {t[2*w+1]:8d} cycles, blocked at barriers {t[2*w]:8d} = {100.0*t[2*w]/t[2*w+1]:.1f} %")
+if t[48]:
+    print(f"serial warp 0: first pass {t[48]} cycles, second pass {t[49]}, Arnoldi sweeps {t[50]} (sum over its rounds)")
