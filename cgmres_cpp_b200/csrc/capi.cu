@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <omp.h>
+
 #include <atomic>
 #include <new>
 #include <string>
@@ -65,6 +67,12 @@ static int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace cgmres_b200
 
 using namespace cgmres_b200;
+
+static int sm_count_of(int device) {
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+  return v;
+}
 
 struct cgmres_b200_controller {
   int model = 0, mode = 0, device = 0;
@@ -275,6 +283,10 @@ struct cgmres_b200_controller {
 template <class Sim>
 static void plant_host(int64_t n, double* x, const double* u) {  // Euler: mul(dxdt,dxdt,dt); add(x,x,dxdt)
   constexpr int nx = Sim::dim_x, nu = Sim::dim_u;
+  // instances are independent: big batches are split over a few host threads (OMP_NUM_THREADS caps it; torchrun
+  // sets that to 1 per rank)
+  const int cap = omp_get_max_threads() < 8 ? omp_get_max_threads() : 8;
+#pragma omp parallel for schedule(static) num_threads(cap) if (n >= 16384)
   for (int64_t i = 0; i < n; i++) plant_euler<Sim>(x + i * nx, u + i * nu);
 }
 
@@ -489,7 +501,12 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
   const int nx = h->mi->dim_x, nu = h->mi->dim_u;
   if (!h->soa()) {  // instance-major state == ABI layout: x straight into place, u straight out
     if (n == 0) return 0;
-    const int S = (h->n >= 8192) ? cgmres_b200_controller::kSlices : 1;
+    // slices are whole "waves" (the instances all SMs hold at once) so that no slice ends in a partly filled wave
+    const int64_t wave = (int64_t)onchip_instances_per_cta(h->model, h->mode) * sm_count_of(h->device);
+    const int64_t waves = (h->n + wave - 1) / wave;
+    const int S = (h->n >= 8192 && waves >= 2)
+                      ? (int)(waves < cgmres_b200_controller::kSlices ? waves : cgmres_b200_controller::kSlices)
+                      : 1;
     if (S == 1) {
       CU(cudaMemcpyAsync(h->x, x, sizeof(double) * n * nx, cudaMemcpyHostToDevice, h->stream));
       int rcu = h->launch_update(0);
@@ -503,11 +520,11 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
     if (rcs) return rcs;
     const double dt_t = h->dtau(h->t), dt_th = h->dtau(h->t + h->mi->h);
     CU(cudaEventRecord(h->ev_begin, h->stream));
-    const int64_t per = (h->n + S - 1) / S;
     for (int i = 0; i < S; i++) {
-      const int64_t lo = (int64_t)i * per;
-      const int64_t cnt = (lo + per <= h->n) ? per : (h->n - lo);
-      if (cnt <= 0) break;
+      const int64_t lo = (waves * i / S) * wave;
+      const int64_t hi_ = (waves * (i + 1) / S) * wave;
+      const int64_t hi = hi_ < h->n ? hi_ : h->n;
+      const int64_t cnt = hi - lo;
       cudaStream_t st = h->side[i];
       CU(cudaStreamWaitEvent(st, h->ev_begin, 0));
       CU(cudaMemcpyAsync(h->x + lo * nx, x + lo * nx, sizeof(double) * (size_t)cnt * nx, cudaMemcpyHostToDevice, st));

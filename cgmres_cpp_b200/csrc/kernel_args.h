@@ -63,6 +63,10 @@ struct FastArgs {
 cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 int fast_instances_per_cta(int model);
+int onchip_exact_instances_per_cta(int model);
+inline int onchip_instances_per_cta(int model, int mode) {  // mode 1 = fast, 2 = onchip_exact (cgmres_b200.h)
+  return mode == 1 ? fast_instances_per_cta(model) : onchip_exact_instances_per_cta(model);
+}
 // doubles of global scratch one launch of the fast kernel over (up to) n instances needs on `device` (0: none)
 size_t fast_scratch_doubles(int model, int device, int64_t n);
 

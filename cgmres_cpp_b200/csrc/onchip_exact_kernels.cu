@@ -37,4 +37,13 @@ cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArg
   return cudaErrorInvalidValue;
 }
 
+int onchip_exact_instances_per_cta(int model) {
+  switch (model) {
+    case MODEL_MSD: return fast::Lay<MassSpringDamperModel>::G;
+    case MODEL_ARM: return fast::Lay<ArmPendulumModel>::G;
+    case MODEL_SEMIACTIVE: return fast::Lay<SemiactiveDamperModel>::G;
+  }
+  return 1;
+}
+
 }  // namespace cgmres_b200
