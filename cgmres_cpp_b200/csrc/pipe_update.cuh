@@ -36,6 +36,12 @@
 namespace cgmres_b200 {
 namespace pipe {
 
+// groups in flight per SM.  The small models would fit three or four (each with its own serial warp), measured
+// slower: semiactive 1.29e8 with 3 vs 1.45e8 with 2, arm 1.4e7 vs 1.95e7 (three or four serial warps share one
+// scheduler, and fewer basis vectors fit in tensor memory).
+#ifndef CG_PIPE_NGMAX
+#define CG_PIPE_NGMAX 2
+#endif
 #ifndef CG_PIPE_GI
 #define CG_PIPE_GI 16  // instances per group = vector warps per CTA
 #endif
@@ -46,7 +52,13 @@ struct Lay {
   static constexpr int nx = F::nx, nu = F::nu, np = F::np, dv = F::dv, km = F::km, L = F::L, np1 = F::np1;
   static constexpr int SXT = F::SXT, XT = F::XT, LTN = F::LTN, Q = F::Q;
   static_assert(F::SU == nu, "pipelined kernel assumes unpadded dim_u rows");
-  static constexpr int GI = CG_PIPE_GI, NG = 2, NI = GI * NG;
+  static constexpr int GI = CG_PIPE_GI;
+  // groups in flight per SM: as many as fit in shared memory (each brings its own serial warp), at most CG_PIPE_NGMAX
+  static constexpr int raw_ = L + XT + LTN + (km * (km + 1) / 2 + 3 * km + 3 * nx + np1 + 2 + km + 1 + 2);
+  static constexpr int stride_ = (raw_ % 2 == 0) ? raw_ + 1 : raw_;
+  static constexpr int NG_fit = (fast::kSmemBudget - 64) / (GI * stride_ * 8);
+  static constexpr int NG = NG_fit < 2 ? 2 : (NG_fit > CG_PIPE_NGMAX ? CG_PIPE_NGMAX : NG_fit);
+  static constexpr int NI = GI * NG;
   static constexpr int NVEC = km + 1;  // stored vectors per instance: id 0 = F1, id 1+i = v_i
   // tensor memory: 2*Q columns per vector; warps w, w+4, ... share a lane quarter
   static constexpr int tcols_vec = 2 * Q;
@@ -87,6 +99,7 @@ struct Lay {
   static constexpr int sCount = sXO + nx;
   static constexpr int raw = oS + sCount;
   static constexpr int stride = (raw % 2 == 0) ? raw + 1 : raw;
+  static_assert(stride == stride_, "keep raw_ in step with the scalar slots");
   static constexpr int threads = 32 * NW;
   static constexpr int bar_threads = 32 * (GI + 1);  // participants of the named barriers: vector warps + serial warp
   static constexpr size_t smem_bytes = (size_t)NI * stride * 8 + 64;
