@@ -116,11 +116,21 @@ struct Lay {
 #define CG_PIPE_WAIT_END(acc)                                   \
   do {                                                          \
     if (*(volatile double*)sm == 1.2345e300) (acc) += 1;        \
-    (acc) += clock64() - t_wait0_;                              \
+    t_lap = clock64();                                          \
+    (acc) += t_lap - t_wait0_;                                  \
+  } while (0)
+#define CG_PIPE_LAP(acc)                  \
+  do {                                    \
+    const long long t_now_ = clock64();   \
+    (acc) += t_now_ - t_lap;              \
+    t_lap = t_now_;                       \
   } while (0)
 #define CG_PIPE_WORK_BEGIN const long long t_work0_ = clock64()
 #define CG_PIPE_WORK_END(acc) (acc) += clock64() - t_work0_
 #else
+#define CG_PIPE_LAP(acc) \
+  do {                   \
+  } while (0)
 #define CG_PIPE_WORK_BEGIN \
   do {                     \
   } while (0)
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   double* const scr_cta = a.scratch + (size_t)blockIdx.x * Y::scratch_doubles_per_cta;
 #ifdef CG_PIPE_TIMING
   long long t_wait = 0, t_p1 = 0, t_p2 = 0, t_sw = 0;
+  long long t_lap = 0, t_fin = 0, t_v1 = 0, t_v2 = 0, t_dh = 0, t_w = 0, t_mgs = 0, t_hh = 0, t_fx = 0, t_si = 0;
   const long long t_begin = clock64();
 #endif
 
@@ -488,7 +499,9 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         double* blk = sm + (size_t)(g * GI + vw) * Y::stride;
         const uint32_t tslot = tbase + (uint32_t)(g * Y::tcols_slot);
         double* scr = scr_cta + (size_t)(g * GI + vw) * Y::NSCR * L;
+        CG_PIPE_LAP(t_wait);
         if (r != (int64_t)blockIdx.x) final_update(r - gridDim.x, g);  // overlaps the serial warp's first pass
+        CG_PIPE_LAP(t_fin);
         { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
         if (has) {
           double f1[Q], dd[Q];
@@ -502,6 +515,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           vec_store(0, tslot, scr, f1);
           form_x(blk, a.U + n * (int64_t)L, dd);
         }
+        CG_PIPE_LAP(t_v1);
         bar_arrive(BX(g), T);
       }
 
@@ -562,6 +576,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
             sc[Y::sCODE] = (double)code;
           }
         }
+        CG_PIPE_LAP(t_v2);
         bar_arrive(BX(g), T);
       }
 
@@ -576,8 +591,16 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           const uint32_t tslot = tbase + (uint32_t)(g * Y::tcols_slot);
           double* scr = scr_cta + (size_t)(g * GI + vw) * Y::NSCR * L;
           { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
+          if (k == km - 2 && more) {  // next round's U and dUdt of this (warp, group): start the HBM reads now
+            const int64_t nn = r_next * NI + (int64_t)g * GI + vw;
+            if (nn < a.n && lane * 16 < L) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.U + nn * (int64_t)L + lane * 16));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dUdt + nn * (int64_t)L + lane * 16));
+            }
+          }
           if (has && sc[Y::sFLAG] == 0.0) {
             stage_dhdu(blk, sc, n);
+            CG_PIPE_LAP(t_dh);
             double w[Q];
             {
               double f1[Q];
@@ -592,6 +615,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
                 }
               }
             }
+            CG_PIPE_LAP(t_w);
             // modified Gram-Schmidt (gmres.hpp:52-58)
             double hc[km + 2];
 #pragma unroll
@@ -615,8 +639,20 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
 #pragma unroll
             for (int q = 0; q < Q; q++) part += w[q] * w[q];
             const double hn = sqrt(fast::warp_sum(part));  // gmres.hpp:59-60
+            CG_PIPE_LAP(t_mgs);
             int code = EXIT_FULL, ncol = k;
             bool solving = true;
+            // U for the next sweep's input U + h*v_{k+1}: requested now, consumed after the reflector / residual
+            // scalars below, whose dependent sqrt / reciprocal chain hides the L2 round trip
+            double un[Q];
+            if (k + 1 < km) {
+              const double* __restrict__ Ug = a.U + n * (int64_t)L;
+#pragma unroll
+              for (int q = 0; q < Q; q++) {
+                const int j = lane + 32 * q;
+                un[q] = (j < L) ? Ug[j] : 0.0;
+              }
+            }
             if (fabs(hn) < DBL_EPSILON) {  // gmres.hpp:63-65
               code = EXIT_BREAKDOWN;
               solving = false;
@@ -667,7 +703,18 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
               sc[Y::sFLAG] = solving ? 0.0 : 1.0;
               sc[Y::sCODE] = (double)(code | (ncol << 8));
             }
-            if (solving && k + 1 < km) form_x(blk, a.U + n * (int64_t)L, w);  // input of the next sweep
+            CG_PIPE_LAP(t_hh);
+            if (solving && k + 1 < km) {  // input of the next sweep (cgmres.hpp:168-169)
+#pragma unroll
+              for (int q = 0; q < Q; q++) {
+                const int j = lane + 32 * q;
+                if (j < L) {
+                  const double t = w[q] * hh;
+                  blk[Y::oX + j] = t + un[q];
+                }
+              }
+            }
+            CG_PIPE_LAP(t_fx);
             __syncwarp();
           }
           if (k + 1 < km) {
@@ -678,7 +725,9 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
             if (has && lane < nx) sc[Y::sXO + lane] = sc[Y::sX + lane];
             __syncwarp();
             if (more) {  // next round's state in, so that the serial warp never waits for a whole round to drain
+              CG_PIPE_LAP(t_hh);
               state_in(r_next, g);
+              CG_PIPE_LAP(t_si);
               bar_arrive(BX(g), T);
             }
           }
@@ -698,6 +747,17 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
       a.dbg[48] = t_p1;
       a.dbg[49] = t_p2;
       a.dbg[50] = t_sw;
+    }
+    if (wid == 1) {  // vector warp 0: cycles per phase of its steps (both groups, all rounds)
+      a.dbg[51] = t_fin;
+      a.dbg[52] = t_v1;
+      a.dbg[53] = t_v2;
+      a.dbg[54] = t_dh;
+      a.dbg[55] = t_w;
+      a.dbg[56] = t_mgs;
+      a.dbg[57] = t_hh;
+      a.dbg[58] = t_fx;
+      a.dbg[59] = t_si;
     }
   }
 #endif

@@ -30,3 +30,10 @@ for w in range(24):
         print(f"warp {w:2d} ({role}): total {t[2*w+1]:8d} cycles, blocked at barriers {t[2*w]:8d} = {100.0*t[2*w]/t[2*w+1]:.1f} %")
 if t[48]:
     print(f"serial warp 0: first pass {t[48]} cycles, second pass {t[49]}, Arnoldi sweeps {t[50]} (sum over its rounds)")
+if t[51] or t[54]:
+    names = ["final update (deferred)", "after pass 1: F1 -> TMEM, U + h*dUdt", "after pass 2: dHdu, b, r0, v0, U + h*v0",
+             "Arnoldi: stage-parallel dHdu", "Arnoldi: (F - F1)/h", "Arnoldi: Gram-Schmidt + norm",
+             "Arnoldi: reflectors, v store, flags", "Arnoldi: U + h*v (next sweep input)", "state in (next round)"]
+    tot = sum(int(t[51 + i]) for i in range(9))
+    for i, nm in enumerate(names):
+        print(f"vector warp 0: {nm:45s} {t[51+i]:9d} cycles  {100.0*t[51+i]/tot:5.1f} %")
