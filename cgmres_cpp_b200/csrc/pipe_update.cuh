@@ -591,13 +591,6 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           const uint32_t tslot = tbase + (uint32_t)(g * Y::tcols_slot);
           double* scr = scr_cta + (size_t)(g * GI + vw) * Y::NSCR * L;
           { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
-          if (k == km - 2 && more) {  // next round's U and dUdt of this (warp, group): start the HBM reads now
-            const int64_t nn = r_next * NI + (int64_t)g * GI + vw;
-            if (nn < a.n && lane * 16 < L) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.U + nn * (int64_t)L + lane * 16));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dUdt + nn * (int64_t)L + lane * 16));
-            }
-          }
           if (has && sc[Y::sFLAG] == 0.0) {
             stage_dhdu(blk, sc, n);
             CG_PIPE_LAP(t_dh);
