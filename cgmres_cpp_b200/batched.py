@@ -26,7 +26,7 @@ import numpy as np
 from ._lib import CgmresB200Error, check, lib
 
 MSD, ARM, SEMIACTIVE = 0, 1, 2
-MODE_EXACT, MODE_FAST, MODE_ONCHIP_EXACT = 0, 1, 2
+MODE_EXACT, MODE_FAST, MODE_ONCHIP_EXACT, MODE_PIPELINED_EXACT = 0, 1, 2, 3
 EXIT_FULL, EXIT_CONVERGED, EXIT_RHO0, EXIT_BREAKDOWN = 0, 1, 2, 3
 
 

@@ -134,10 +134,11 @@ struct cgmres_b200_controller {
       if ((rc = dalloc(&u_out, l * mi->dim_u))) return rc;
       if ((rc = dalloc(&status, l))) return rc;
       if ((rc = dalloc(&dbg, 64))) return rc;
-      if (mode == CGMRES_B200_MODE_FAST) {  // region 0: full-batch launches; 1..kSlices: the pipelined slices
-        scratch_region = fast_scratch_doubles(model, device, n);
-        if (scratch_region && (rc = dalloc(&scratch, scratch_region * (size_t)(kSlices + 1)))) return rc;
-      }
+      // spill regions of the pipelined kernel: region 0 for full-batch launches, 1..kSlices for the slices
+      scratch_region = (mode == CGMRES_B200_MODE_FAST)              ? fast_scratch_doubles(model, device, n)
+                       : (mode == CGMRES_B200_MODE_PIPELINED_EXACT) ? pipelined_exact_scratch_doubles(model, device, n)
+                                                                    : 0;
+      if (scratch_region && (rc = dalloc(&scratch, scratch_region * (size_t)(kSlices + 1)))) return rc;
       if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;
       return 0;
     }
@@ -205,6 +206,8 @@ struct cgmres_b200_controller {
     f.scratch = scratch ? scratch + scratch_region * (size_t)region : nullptr;
     if (mode == CGMRES_B200_MODE_FAST)
       CU(fast_launch_control(model, ptau_full, f, s));
+    else if (mode == CGMRES_B200_MODE_PIPELINED_EXACT)
+      CU(pipelined_exact_launch_control(model, ptau_full, f, s));
     else
       CU(onchip_exact_launch_control(model, ptau_full, f, s));
     g_launches++;
@@ -338,7 +341,8 @@ int cgmres_b200_create(int model, int64_t n, int device, int mode, cgmres_b200_h
   const ModelInfo* mi = model_info(model);
   if (!mi) return fail(CGMRES_B200_EINVAL, "unknown model id");
   if (n < 0) return fail(CGMRES_B200_EINVAL, "negative instance count");
-  if (mode != CGMRES_B200_MODE_EXACT && mode != CGMRES_B200_MODE_FAST && mode != CGMRES_B200_MODE_ONCHIP_EXACT)
+  if (mode != CGMRES_B200_MODE_EXACT && mode != CGMRES_B200_MODE_FAST && mode != CGMRES_B200_MODE_ONCHIP_EXACT &&
+      mode != CGMRES_B200_MODE_PIPELINED_EXACT)
     return fail(CGMRES_B200_EINVAL, "unknown mode");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);

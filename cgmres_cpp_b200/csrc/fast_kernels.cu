@@ -8,7 +8,7 @@
 #define CG_SWEEP_UNROLL 10
 #endif
 #include "fast_update.cuh"
-#include "pipe_update.cuh"
+#include "pipe_launch.cuh"
 
 // experiment knob (tools/sweep_build.sh): build the "fast" entry point with the reference's sequential sums
 #ifndef CG_FAST_SEQ_SUMS
@@ -30,40 +30,9 @@
 
 namespace cgmres_b200 {
 namespace {
-int sm_count(int device) {
-  static int cached[64] = {0};
-  if (device < 0 || device >= 64) device = 0;
-  if (cached[device] == 0) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
-    cached[device] = v;
-  }
-  return cached[device];
-}
-
 template <class M, class Sim>
 cudaError_t launch_pipe(bool pfull, const FastArgs& a, cudaStream_t s) {
-  using Y = pipe::Lay<M>;
-  if (a.n == 0) return cudaSuccess;
-  if (a.scratch == nullptr) return cudaErrorInvalidValue;
-  int device = 0;
-  cudaError_t e = cudaGetDevice(&device);
-  if (e != cudaSuccess) return e;
-  const int64_t rounds = (a.n + Y::NI - 1) / Y::NI;
-  const int sms = sm_count(device);
-  const unsigned grid = (unsigned)(rounds < (int64_t)sms ? rounds : (int64_t)sms);  // persistent: one CTA per SM
-  if (pfull) {
-    e = cudaFuncSetAttribute(pipe::control_kernel<M, Sim, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Y::smem_bytes);
-    if (e != cudaSuccess) return e;
-    pipe::control_kernel<M, Sim, true><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(pipe::control_kernel<M, Sim, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Y::smem_bytes);
-    if (e != cudaSuccess) return e;
-    pipe::control_kernel<M, Sim, false><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
-  }
-  return cudaGetLastError();
+  return pipe::launch<M, Sim, false>(pfull, a, s);
 }
 
 template <class M, class Sim>
@@ -102,21 +71,11 @@ cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cu
   return cudaErrorInvalidValue;
 }
 
-namespace {
-template <class M>
-size_t scratch_for(int device, int64_t n) {
-  using Y = pipe::Lay<M>;
-  const int64_t rounds = (n + Y::NI - 1) / Y::NI;
-  const int64_t ctas = rounds < (int64_t)sm_count(device) ? rounds : (int64_t)sm_count(device);
-  return (size_t)(ctas > 0 ? ctas : 1) * Y::scratch_doubles_per_cta;
-}
-}  // namespace
-
 size_t fast_scratch_doubles(int model, int device, int64_t n) {
   switch (model) {
-    case MODEL_MSD: return CG_FAST_PIPE_MSD ? scratch_for<MassSpringDamperModel>(device, n) : 0;
-    case MODEL_ARM: return CG_FAST_PIPE_ARM ? scratch_for<ArmPendulumModel>(device, n) : 0;
-    case MODEL_SEMIACTIVE: return CG_FAST_PIPE_SEMI ? scratch_for<SemiactiveDamperModel>(device, n) : 0;
+    case MODEL_MSD: return CG_FAST_PIPE_MSD ? pipe::scratch_for<MassSpringDamperModel>(device, n) : 0;
+    case MODEL_ARM: return CG_FAST_PIPE_ARM ? pipe::scratch_for<ArmPendulumModel>(device, n) : 0;
+    case MODEL_SEMIACTIVE: return CG_FAST_PIPE_SEMI ? pipe::scratch_for<SemiactiveDamperModel>(device, n) : 0;
   }
   return 0;
 }

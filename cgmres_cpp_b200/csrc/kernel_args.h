@@ -62,13 +62,16 @@ struct FastArgs {
 // exact_kernels.cu (bit-identical to the reference; verification build of the same kernel)
 cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
+// the fast mode's persistent pipelined kernel built with sequential sums and no FMA (onchip_exact_kernels.cu)
+cudaError_t pipelined_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 int fast_instances_per_cta(int model);
 int onchip_exact_instances_per_cta(int model);
-inline int onchip_instances_per_cta(int model, int mode) {  // mode 1 = fast, 2 = onchip_exact (cgmres_b200.h)
-  return mode == 1 ? fast_instances_per_cta(model) : onchip_exact_instances_per_cta(model);
+inline int onchip_instances_per_cta(int model, int mode) {  // mode 1 = fast, 2 = onchip_exact, 3 = pipelined exact
+  return mode == 2 ? onchip_exact_instances_per_cta(model) : fast_instances_per_cta(model);
 }
 // doubles of global scratch one launch of the fast kernel over (up to) n instances needs on `device` (0: none)
 size_t fast_scratch_doubles(int model, int device, int64_t n);
+size_t pipelined_exact_scratch_doubles(int model, int device, int64_t n);
 
 // exact mode (exact_kernels.cu)
 cudaError_t exact_launch_control(int model, bool ptau_full, const ExactArgs& a, cudaStream_t s);

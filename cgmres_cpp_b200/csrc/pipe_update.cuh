@@ -168,7 +168,12 @@ __device__ __forceinline__ double ld_keep(const double* p, uint64_t pol) {
   return v;
 }
 
-template <class M, class Sim, bool PFULL>
+// EXACT = true (instantiated only in the -fmad=false translation unit; the ABI's PIPELINED_EXACT verification mode):
+// every dot product and norm is the reference's sequential sum (matrix.hpp:140-159) -- the owning warp parks the
+// element products in the instance's (free) X buffer and lane 0 adds them in index order -- and the kernel is
+// bit-identical to the reference.  It proves that the fast build differs from a bit-exact kernel in nothing but FMA
+// contraction and the order of those sums.
+template <class M, class Sim, bool PFULL, bool EXACT = false>
 __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastArgs a) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, L = Y::L, km = Y::km, Q = Y::Q, GI = Y::GI, NG = Y::NG, NI = Y::NI;
@@ -315,6 +320,32 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           blk[Y::oX + j] = t + uu[q];
         }
       }
+    };
+
+    // EXACT: sum_{j=0..L-1} prod_j in index order, starting from 0 (the reference's loop); X is free whenever
+    // this is called.  Loads of a batch are issued together, the adds keep their order.
+    auto seq_sum = [&](double* blk, const double* prod) -> double {
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        const int j = lane + 32 * q;
+        if (j < L) blk[Y::oX + j] = prod[q];
+      }
+      __syncwarp();
+      double acc = 0.0;
+      if (lane == 0) {
+        constexpr int BS = 10;
+        for (int j0 = 0; j0 + BS <= L; j0 += BS) {
+          double v[BS];
+#pragma unroll
+          for (int q = 0; q < BS; q++) v[q] = blk[Y::oX + j0 + q];
+#pragma unroll
+          for (int q = 0; q < BS; q++) acc += v[q];
+        }
+        for (int j = (L / BS) * BS; j < L; j++) acc += blk[Y::oX + j];
+      }
+      acc = __shfl_sync(0xffffffffu, acc, 0);
+      __syncwarp();
+      return acc;
     };
 
     // stage-parallel dHdu (cgmres.hpp:156-161), one stage per lane; F_i overwrites u_i in X
@@ -552,10 +583,18 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
               double ax = fc - fa[q];  // cgmres.hpp:173-174
               ax = ax * inv_h;
               w[q] = b - ax;  // gmres.hpp:34
-              ssq += w[q] * w[q];
+              if (!EXACT) ssq += w[q] * w[q];
             }
           }
-          const double rho0 = sqrt(fast::warp_sum(ssq));  // gmres.hpp:37
+          if (EXACT) {
+            double pr[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) pr[q] = w[q] * w[q];
+            ssq = seq_sum(blk, pr);
+          } else {
+            ssq = fast::warp_sum(ssq);
+          }
+          const double rho0 = sqrt(ssq);  // gmres.hpp:37
           int code = EXIT_FULL;
           bool solving = true;
           if (rho0 < M::tol) {  // gmres.hpp:39-41
@@ -617,10 +656,18 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
             for (int i = 0; i <= k; i++) {
               double c[Q];
               vec_load(1 + i, tslot, scr, c);
-              double part = 0.0;
+              double hik;
+              if (EXACT) {
+                double pr[Q];
 #pragma unroll
-              for (int q = 0; q < Q; q++) part += c[q] * w[q];  // slots beyond L hold zeros in both
-              const double hik = fast::warp_sum(part);
+                for (int q = 0; q < Q; q++) pr[q] = c[q] * w[q];
+                hik = seq_sum(blk, pr);
+              } else {
+                double part = 0.0;
+#pragma unroll
+                for (int q = 0; q < Q; q++) part += c[q] * w[q];  // slots beyond L hold zeros in both
+                hik = fast::warp_sum(part);
+              }
               hc[i] = hik;
 #pragma unroll
               for (int q = 0; q < Q; q++) {
@@ -629,9 +676,17 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
               }
             }
             double part = 0.0;
+            if (EXACT) {
+              double pr[Q];
 #pragma unroll
-            for (int q = 0; q < Q; q++) part += w[q] * w[q];
-            const double hn = sqrt(fast::warp_sum(part));  // gmres.hpp:59-60
+              for (int q = 0; q < Q; q++) pr[q] = w[q] * w[q];
+              part = seq_sum(blk, pr);
+            } else {
+#pragma unroll
+              for (int q = 0; q < Q; q++) part += w[q] * w[q];
+              part = fast::warp_sum(part);
+            }
+            const double hn = sqrt(part);  // gmres.hpp:59-60
             CG_PIPE_LAP(t_mgs);
             int code = EXIT_FULL, ncol = k;
             bool solving = true;

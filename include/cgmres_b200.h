@@ -47,8 +47,10 @@ enum {
   CGMRES_B200_MODE_FAST = 1,  /* persistent on-chip kernel (instance groups resident in shared / tensor memory,
                                  serial-recursion and vector warps pipelined), FMA + shuffle reductions: within
                                  the north-star tolerances                                                  */
-  CGMRES_B200_MODE_ONCHIP_EXACT = 2 /* on-chip kernel (one CTA per instance group) with the reference's sequential
+  CGMRES_B200_MODE_ONCHIP_EXACT = 2, /* on-chip kernel (one CTA per instance group) with the reference's sequential
                                  sums and no FMA: bit-identical like MODE_EXACT                             */
+  CGMRES_B200_MODE_PIPELINED_EXACT = 3 /* verification build of the MODE_FAST kernel: same persistent pipelined
+                                 kernel, sequential sums, no FMA: bit-identical (slower than mode 2)          */
 };
 
 /* status word of an instance's last update: exit code in bits 0..7, Krylov columns used in bits 8..15 */

@@ -26,11 +26,17 @@ def cg(built):
     return m
 
 
-# ---------------------------------------------------------------- on-chip kernel, exact arithmetic
+# ---------------------------------------------------------------- on-chip kernels, exact arithmetic
+# MODE_ONCHIP_EXACT = the first-generation on-chip kernel; MODE_PIPELINED_EXACT = the FAST mode's persistent pipelined
+# kernel built with sequential sums and no FMA: everything below must be bit-identical for both
+EXACT_ONCHIP = ["MODE_ONCHIP_EXACT", "MODE_PIPELINED_EXACT"]
+
+
+@pytest.mark.parametrize("mode_name", EXACT_ONCHIP)
 @pytest.mark.parametrize("model", MODELS)
-def test_onchip_exact_golden_batch_1000_steps(cg, model):
+def test_onchip_exact_golden_batch_1000_steps(cg, model, mode_name):
     g = gold(model)
-    c, un = make(cg, model, g["batch_x0"], g["batch_p"], g["batch_u0"], mode=cg.MODE_ONCHIP_EXACT)
+    c, un = make(cg, model, g["batch_x0"], g["batch_p"], g["batch_u0"], mode=getattr(cg, mode_name))
     for r in range(10):
         c.step_closed_loop(100)
         x, u = c.get_x(), c.get_u()
@@ -45,13 +51,14 @@ def test_onchip_exact_golden_batch_1000_steps(cg, model):
     c.close()
 
 
+@pytest.mark.parametrize("mode_name", EXACT_ONCHIP)
 @pytest.mark.parametrize("model", [po.MSD, po.SEMIACTIVE])
 @pytest.mark.parametrize("n", [1, 7, 45])
-def test_onchip_exact_ragged_batches_match_oracle(cg, oracle_best, model, n):
-    """n not a multiple of the instances-per-CTA group (partial last CTA)."""
+def test_onchip_exact_ragged_batches_match_oracle(cg, oracle_best, model, n, mode_name):
+    """n not a multiple of the instances-per-CTA group (partial last CTA / partly filled groups)."""
     x0, p, u0 = po.synthetic_batch(model, n, seed=31 + n)
     want = oracle_best.run_closed_loop(model, x0, p, u0, 120, want_U=True)
-    c, _ = make(cg, model, x0, p, u0, mode=cg.MODE_ONCHIP_EXACT)
+    c, _ = make(cg, model, x0, p, u0, mode=getattr(cg, mode_name))
     c.step_closed_loop(120)
     assert np.array_equal(c.get_x(), want["x_fin"])
     t, U, dUdt = c.get_state()
@@ -59,7 +66,8 @@ def test_onchip_exact_ragged_batches_match_oracle(cg, oracle_best, model, n):
     c.close()
 
 
-def test_onchip_exact_exit_paths_on_long_msd_run(cg, oracle_port):
+@pytest.mark.parametrize("mode_name", EXACT_ONCHIP)
+def test_onchip_exact_exit_paths_on_long_msd_run(cg, oracle_port, mode_name):
     """Early convergence (one column dropped) and rho0<tol stale-dUdt returns (0-4): the shipped msd
     run reaches them after step 11 875 / 13 286.  The oracle runs the first 11 800 steps, the GPU takes over its
     checkpoint {t,U,dUdt,x} and both continue for 2 400 steps; exit path, columns used and state must agree."""
@@ -70,7 +78,7 @@ def test_onchip_exact_exit_paths_on_long_msd_run(cg, oracle_port):
     ctl.init_u0_newton(s["u0"], x, s["p"], 10)
     for _ in range(11800):
         oracle_port.plant_step(model, x, ctl.control(x))
-    c = cg.BatchedCgmres(model, 1, mode=cg.MODE_ONCHIP_EXACT)
+    c = cg.BatchedCgmres(model, 1, mode=getattr(cg, mode_name))
     c.set_ptau_repeat([s["p"]])
     t, U, dUdt = ctl.get_state()
     c.set_state(t, U[None], dUdt[None])
@@ -92,14 +100,15 @@ def test_onchip_exact_exit_paths_on_long_msd_run(cg, oracle_port):
 
 
 
-def test_onchip_exact_time_varying_reference_and_host_api(cg, oracle_best):
+@pytest.mark.parametrize("mode_name", EXACT_ONCHIP)
+def test_onchip_exact_time_varying_reference_and_host_api(cg, oracle_best, mode_name):
     model, n = po.MSD, 13
     dm = oracle_best.dims(model)
     x0, p, u0 = po.synthetic_batch(model, n, seed=5)
     ramp = np.linspace(0.0, 0.3, dm.dv + 1)[None, :, None]
     pfull = np.ascontiguousarray((p[:, None, :] + ramp).reshape(n, -1))
     want = oracle_best.run_closed_loop(model, x0, pfull, u0, 60, p_full=True, want_U=True)
-    c, _ = make(cg, model, x0, pfull, u0, mode=cg.MODE_ONCHIP_EXACT, ptau_full=True)
+    c, _ = make(cg, model, x0, pfull, u0, mode=getattr(cg, mode_name), ptau_full=True)
     x = x0.copy()
     for _ in range(60):  # host-buffer API like the reference's main()
         u = c.control(x)
@@ -170,6 +179,21 @@ def test_fast_group_and_round_edges_track_the_bit_exact_kernel(cg, model, n):
     assert np.abs(xf - xe).max() <= TOL_X_ABS
     assert rel_inf(Uf, Ue) <= 1e-6 and rel_inf(uf, ue) <= 1e-6
     assert np.array_equal(cf, ce) and np.array_equal(kf, ke)
+
+
+def test_pipelined_exact_equals_first_generation_kernel_on_multi_round_batch(cg):
+    """9481 instances = several rounds per persistent CTA with a ragged tail: the pipelined kernel's exact build
+    must equal the first-generation on-chip kernel bit for bit (x, u, U, dUdt, exit status)."""
+    model, n, steps = po.MSD, 9481, 40
+    x0, p, u0 = po.synthetic_batch(model, n, seed=77)
+    got = {}
+    for mode in (cg.MODE_PIPELINED_EXACT, cg.MODE_ONCHIP_EXACT):
+        c, _ = make(cg, model, x0, p, u0, mode=mode)
+        c.step_closed_loop(steps)
+        got[mode] = (c.get_x(), c.get_u(), c.get_state()[1], c.get_state()[2], *c.get_status())
+        c.close()
+    for a, b in zip(got[cg.MODE_PIPELINED_EXACT], got[cg.MODE_ONCHIP_EXACT]):
+        assert np.array_equal(a, b)
 
 
 def test_fast_exit_paths_on_long_msd_run(cg, oracle_port):
