@@ -39,7 +39,7 @@ HBM_BYTES_PER_UPDATE = {"msd": 9728, "arm": 2504, "semiactive": 4856}  # read U,
 # fastest mode per model that meets the parity bars: the on-chip TMEM kernel for the models
 # whose time is in the Krylov vector work, the streaming thread-per-instance kernel for the sin/cos-heavy arm model
 DEFAULT_MODE = {"msd": "fast", "semiactive": "fast", "arm": "exact"}
-MODE_IDS = {"exact": 0, "fast": 1, "onchip_exact": 2}
+MODE_IDS = {"exact": 0, "fast": 1, "onchip_exact": 2, "pipelined_exact": 3}
 
 
 def workload_name(model: str, n_per_gpu: int, steps: int) -> str:
@@ -246,7 +246,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if world == 1 and not args.no_other_modes:
         probe_n, probe_steps = min(n, 4096), 100
         ref_x = None
-        for name in ("onchip_exact", "exact", "fast"):
+        for name in ("onchip_exact", "pipelined_exact", "exact", "fast"):
             c2 = cg.BatchedCgmres(model_id, n, device=local_rank, mode=MODE_IDS[name])
             c2.set_stream(stream.cuda_stream)
             c2.set_ptau_repeat(p)
@@ -309,7 +309,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "p50_per_update_latency_us": p50_ms * 1e3 / n,
             "roofline": {
                 "bound": "fp64", "achieved": flops, "peak": peak_fma, "unit": "TFLOP/s", "frac": flops / peak_fma,
-                "traffic": traffic, "kernel": "%s::control_kernel (one launch = one control update + plant step per instance)" % {"exact": "exact", "onchip_exact": "fast", "fast": "pipe"}.get(args.mode, args.mode),
+                "traffic": traffic, "kernel": "%s::control_kernel (one launch = one control update + plant step per instance)" % {"exact": "exact", "onchip_exact": "fast", "fast": "pipe", "pipelined_exact": "pipe"}.get(args.mode, args.mode),
                 "flop_per_update": FLOP_PER_UPDATE[model], "launch_ms": launch_ms,
                 "peak_source": "measured live: 8 DFMA chains/thread microbenchmark (cgmres_b200_measure_fp64_peak)",
                 "peak_no_fma": peak_nofma, "frac_of_no_fma_peak": flops / peak_nofma,
@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--model", choices=tuple(MODELS), default="msd")
-    ap.add_argument("--mode", choices=("auto", "fast", "onchip_exact", "exact"), default="auto",
+    ap.add_argument("--mode", choices=("auto", "fast", "onchip_exact", "pipelined_exact", "exact"), default="auto",
                     help="auto = the fastest parity-green mode of the model (DEFAULT_MODE)")
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=200)
