@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Phase breakdown of one warp of CTA 0 of the on-chip kernel (library built with EXTRA/FAST_EXTRA=-DCG_FAST_TIMING)."""
+"""Phase breakdown of one warp of CTA 0 of the first-generation on-chip kernel (fast_update.cuh; library built with
+EXTRA=-DCG_FAST_TIMING; it now serves MODE_ONCHIP_EXACT).  For the pipelined fast-mode kernel see
+tools/pipe_wait_times.py (FAST_EXTRA=-DCG_PIPE_TIMING)."""
 import ctypes as C
 import os
 import sys
@@ -14,7 +16,7 @@ from cgmres_cpp_b200 import workloads as po  # noqa: E402
 model = {"msd": 0, "arm": 1, "semiactive": 2}[sys.argv[1] if len(sys.argv) > 1 else "msd"]
 n = 65536
 x0, p, u0 = po.synthetic_batch(model, n)
-c = cg.BatchedCgmres(model, n, mode=cg.MODE_FAST)
+c = cg.BatchedCgmres(model, n, mode=cg.MODE_ONCHIP_EXACT)
 c.set_ptau_repeat(p); c.init_u0(u0); c.init_u0_newton(u0, x0, p, 10); c.set_x(x0)
 c.step_closed_loop(20)
 c.synchronize()
