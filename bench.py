@@ -29,6 +29,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# Host threads of the e2e loop's plant step (cgmres_b200_plant_step_host, OpenMP): under torchrun every rank gets
+# its share of the box's cores instead of torchrun's blanket OMP_NUM_THREADS=1.  Must happen before libgomp loads.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    _lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, _lws)))
+
 METRIC = "batched C/GMRES control updates/sec"
 UNIT = "updates/s"
 MODELS = {"msd": 0, "arm": 1, "semiactive": 2}
