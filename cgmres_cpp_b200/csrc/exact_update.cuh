@@ -40,9 +40,11 @@
 #define CG_MAXREG 168
 #endif
 #ifndef CG_B2
-#define CG_B2 16  // elements per load batch, passes with 2 streams
-#define CG_B3 12  // passes with 3+ streams
-#define CG_BN 24  // norm pass (1 stream)
+// (batch sizes that divide every shipped L = 300 / 150 / 75, so no pass ends in a ragged batch: GPU sweep
+//  16/12/24/5 -> 15/15/25/5: msd 1.99e7 -> 2.01e7, semiactive 4.33e7 -> 4.43e7, arm 8.96e7 -> 9.31e7)
+#define CG_B2 15  // elements per load batch, passes with 2 streams
+#define CG_B3 15  // passes with 3+ streams
+#define CG_BN 25  // norm pass (1 stream)
 #define CG_BF 5   // final pass (7 streams)
 #endif
 
