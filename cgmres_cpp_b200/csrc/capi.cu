@@ -81,9 +81,9 @@ struct cgmres_b200_controller {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   // pipelined host-buffer control(): slices of the batch on side streams so that one slice's PCIe copies overlap
   // another slice's kernel (instance-major modes only; instances are independent, so slicing changes nothing)
-  static constexpr int kSlices = 4;
-  cudaStream_t side[kSlices] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_begin = nullptr, ev_done[kSlices] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kSlices = 5;
+  cudaStream_t side[kSlices] = {};
+  cudaEvent_t ev_begin = nullptr, ev_done[kSlices] = {};
   double t = 0.0;          // cgmres.hpp:195 -- all instances of a handle step in lock step
   bool ptau_full = false;  // false: ptau holds one p per instance (set_ptau_repeat)
   int integrator = PLANT_EULER;  // plant step of step_closed_loop: the reference's Euler, or RK4
@@ -524,9 +524,20 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
     if (rcs) return rcs;
     const double dt_t = h->dtau(h->t), dt_th = h->dtau(h->t + h->mi->h);
     CU(cudaEventRecord(h->ev_begin, h->stream));
+    // slice boundaries in waves: with enough waves the first and the last slice are ONE wave, so that the copies
+    // nothing can overlap (x of the first slice in, u of the last slice out) are as small as possible
+    int64_t wb[cgmres_b200_controller::kSlices + 1];
+    if (S >= 3 && waves >= 2 + (S - 2)) {
+      wb[0] = 0;
+      wb[1] = 1;
+      for (int i = 2; i < S; i++) wb[i] = 1 + (waves - 2) * (i - 1) / (S - 2);
+      wb[S] = waves;
+    } else {
+      for (int i = 0; i <= S; i++) wb[i] = waves * i / S;
+    }
     for (int i = 0; i < S; i++) {
-      const int64_t lo = (waves * i / S) * wave;
-      const int64_t hi_ = (waves * (i + 1) / S) * wave;
+      const int64_t lo = wb[i] * wave;
+      const int64_t hi_ = wb[i + 1] * wave;
       const int64_t hi = hi_ < h->n ? hi_ : h->n;
       const int64_t cnt = hi - lo;
       cudaStream_t st = h->side[i];
