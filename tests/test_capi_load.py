@@ -21,6 +21,24 @@ def test_header_and_binding_table_agree(built):
     assert declared_symbols() == sorted(SIGNATURES)
 
 
+def test_header_enums_match_the_python_mirror(built):
+    """Model ids, build modes, exit codes and plant integrators: the numbers in include/cgmres_b200.h are the
+    numbers cgmres_cpp_b200 uses."""
+    import cgmres_cpp_b200 as cg
+
+    src = open(os.path.join(ROOT, "include", "cgmres_b200.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(CGMRES_B200_[A-Z0-9_]+)\s*=\s*(-?\d+)", src)}
+    assert enums["CGMRES_B200_MODEL_MASS_SPRING_DAMPER"] == cg.MSD
+    assert enums["CGMRES_B200_MODEL_ARM_TYPE_INVERTED_PENDULUM"] == cg.ARM
+    assert enums["CGMRES_B200_MODEL_SEMIACTIVE_DAMPER"] == cg.SEMIACTIVE
+    assert enums["CGMRES_B200_MODE_EXACT"] == cg.MODE_EXACT
+    assert enums["CGMRES_B200_MODE_FAST"] == cg.MODE_FAST
+    assert enums["CGMRES_B200_MODE_ONCHIP_EXACT"] == cg.MODE_ONCHIP_EXACT
+    assert enums["CGMRES_B200_MODE_PIPELINED_EXACT"] == cg.MODE_PIPELINED_EXACT
+    assert (enums["CGMRES_B200_EXIT_FULL"], enums["CGMRES_B200_EXIT_CONVERGED"], enums["CGMRES_B200_EXIT_RHO0"],
+            enums["CGMRES_B200_EXIT_BREAKDOWN"]) == (cg.EXIT_FULL, cg.EXIT_CONVERGED, cg.EXIT_RHO0, cg.EXIT_BREAKDOWN)
+
+
 def test_library_exports_every_declared_symbol(built):
     from cgmres_cpp_b200._lib import LIB_PATH
 
