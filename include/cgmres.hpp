@@ -27,19 +27,72 @@
 #include "gmres.hpp"
 
 namespace cgmres_b200 {
+// Which compiled kernel serves a host-side Model class.  The kernels are compiled per problem into
+// libcgmres_b200.so, so the template argument only has to NAME one of them:
+//  * the functors of cgmres_b200/models.hpp (and the per-example headers of this include tree that export them
+//    as Model / Model1 / Model2) map directly;
+//  * any other class with the reference's Model contract -- in particular the reference's own
+//    <example>/model.hpp, which an unmodified main.cpp picks up from its own directory -- is identified by its
+//    compile-time sizes and parameters and then PROBED: dxdt, dPhidx, dHdx, dHdu are evaluated on the host at two
+//    fixed points and must agree with the shipped functor (to 1e-12 relative: the arm functor's sin/cos differ
+//    from libm's in the last bit).  A class that matches nothing throws instead of running the wrong problem.
+template <class Ours, class Theirs>
+inline bool same_problem(void) {
+  if (Ours::dim_x != Theirs::dim_x || Ours::dim_u != Theirs::dim_u || Ours::dim_p != Theirs::dim_p ||
+      Ours::dv != Theirs::dv || Ours::k_max != Theirs::k_max)
+    return false;
+  const double pa[6] = {Ours::dt, Ours::h, Ours::zeta, Ours::Tf, Ours::alpha, Ours::tol};
+  const double pb[6] = {Theirs::dt, Theirs::h, Theirs::zeta, Theirs::Tf, Theirs::alpha, Theirs::tol};
+  for (int i = 0; i < 6; i++)
+    if (pa[i] != pb[i]) return false;
+  constexpr int nx = Ours::dim_x, nu = Ours::dim_u, np = Ours::dim_p > 0 ? Ours::dim_p : 1;
+  for (int probe = 0; probe < 2; probe++) {
+    double x[nx], u[nu], p[np], lmd[nx], a[nx > nu ? nx : nu], b[nx > nu ? nx : nu];
+    for (int i = 0; i < nx; i++) x[i] = 0.3 + 0.17 * i - 0.45 * probe, lmd[i] = -0.2 + 0.11 * i + 0.3 * probe;
+    for (int i = 0; i < nu; i++) u[i] = 0.05 + 0.23 * i - 0.1 * probe;
+    for (int i = 0; i < np; i++) p[i] = 0.4 - 0.3 * i;
+    auto agree = [&](int cnt) {
+      for (int i = 0; i < cnt; i++) {
+        const double scale = (a[i] < 0 ? -a[i] : a[i]) + 1.0;
+        const double d = a[i] - b[i];
+        if ((d < 0 ? -d : d) > 1e-12 * scale) return false;
+      }
+      return true;
+    };
+    Ours::dxdt(a, x, u, p), Theirs::dxdt(b, x, u, p);
+    if (!agree(nx)) return false;
+    Ours::dPhidx(a, x, p), Theirs::dPhidx(b, x, p);
+    if (!agree(nx)) return false;
+    Ours::dHdx(a, x, u, p, lmd), Theirs::dHdx(b, x, u, p, lmd);
+    if (!agree(nx)) return false;
+    Ours::dHdu(a, x, u, p, lmd), Theirs::dHdu(b, x, u, p, lmd);
+    if (!agree(nu)) return false;
+  }
+  return true;
+}
+
 template <class Model>
-struct ModelId;
+struct ModelId {
+  static int value(void) {
+    if (same_problem<MassSpringDamperModel, Model>()) return CGMRES_B200_MODEL_MASS_SPRING_DAMPER;
+    if (same_problem<ArmPendulumModel, Model>()) return CGMRES_B200_MODEL_ARM_TYPE_INVERTED_PENDULUM;
+    if (same_problem<SemiactiveDamperModel, Model>()) return CGMRES_B200_MODEL_SEMIACTIVE_DAMPER;
+    throw std::runtime_error(
+        "Cgmres<Model>: no kernel in libcgmres_b200.so was compiled for this Model (add its functor to "
+        "include/cgmres_b200/models.hpp and instantiate the kernels for it)");
+  }
+};
 template <>
 struct ModelId<MassSpringDamperModel> {
-  static constexpr int value = CGMRES_B200_MODEL_MASS_SPRING_DAMPER;
+  static int value(void) { return CGMRES_B200_MODEL_MASS_SPRING_DAMPER; }
 };
 template <>
 struct ModelId<ArmPendulumModel> {
-  static constexpr int value = CGMRES_B200_MODEL_ARM_TYPE_INVERTED_PENDULUM;
+  static int value(void) { return CGMRES_B200_MODEL_ARM_TYPE_INVERTED_PENDULUM; }
 };
 template <>
 struct ModelId<SemiactiveDamperModel> {
-  static constexpr int value = CGMRES_B200_MODEL_SEMIACTIVE_DAMPER;
+  static int value(void) { return CGMRES_B200_MODEL_SEMIACTIVE_DAMPER; }
 };
 inline void check(int rc, const char* what) {
   if (rc != 0) throw std::runtime_error(std::string(what) + ": " + cgmres_b200_last_error());
@@ -50,9 +103,9 @@ template <class Model>
 class Cgmres : public Gmres {
  public:
   // n_instances independent controllers on `device`; the default is the reference's single object.
-  explicit Cgmres(int64_t n_instances = 1, int device = 0, int mode = CGMRES_B200_MODE_EXACT)
+  explicit Cgmres(int64_t n_instances = 1, int device = 0, int mode = CGMRES_B200_MODE_ONCHIP_EXACT)
       : Gmres(len, Model::k_max, Model::tol), n_(n_instances), h_(nullptr) {
-    cgmres_b200::check(cgmres_b200_create(cgmres_b200::ModelId<Model>::value, n_instances, device, mode, &h_),
+    cgmres_b200::check(cgmres_b200_create(cgmres_b200::ModelId<Model>::value(), n_instances, device, mode, &h_),
                        "cgmres_b200_create");
   }
   ~Cgmres(void) { cgmres_b200_destroy(h_); }

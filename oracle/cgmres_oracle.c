@@ -607,7 +607,9 @@ typedef struct {
   const double *x0, *p, *u0;
   double *x_traj, *u_traj, *x_fin, *u_fin, *U_fin, *dUdt_fin, *ctl_seconds;
   int32_t* exit_hist;
+  double loop_seconds; /* wall time this thread spent inside its closed-loop step loops */
 } job_t;
+static double g_last_loop_seconds = 0.0;
 
 static double now_s(void) {
   struct timespec ts;
@@ -636,6 +638,7 @@ static void* worker(void* arg) {
     ORACLE_FN(init_u0)(c, u);
     ORACLE_FN(init_u0_newton)(c, u, x, p0, jb->newton_iters);
     double acc = 0.0;
+    const double loop0 = now_s();
     for (int s = 0; s < jb->n_steps; s++) {
       const double t0 = now_s();
       ORACLE_FN(control)(c, u, x);
@@ -648,6 +651,7 @@ static void* worker(void* arg) {
         if (jb->u_traj) memcpy(jb->u_traj + (r * jb->n + n) * nu, u, sizeof(double) * nu);
       }
     }
+    jb->loop_seconds += now_s() - loop0;
     if (jb->x_fin) memcpy(jb->x_fin + (size_t)nx * n, x, sizeof(double) * nx);
     if (jb->u_fin) memcpy(jb->u_fin + (size_t)nu * n, u, sizeof(double) * nu);
     if (jb->U_fin) memcpy(jb->U_fin + (size_t)L * n, c->U, sizeof(double) * L);
@@ -672,7 +676,7 @@ int ORACLE_FN(run_closed_loop)(int model, int64_t n, const double* x0, const dou
   pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
   for (int t = 0; t < n_threads; t++) {
     job_t jb = {model, p_full, newton_iters, n_steps, rec_stride, t, n_threads, n, x0, p, u0,
-                x_traj, u_traj, x_fin, u_fin, U_fin, dUdt_fin, ctl_seconds, exit_hist};
+                x_traj, u_traj, x_fin, u_fin, U_fin, dUdt_fin, ctl_seconds, exit_hist, 0.0};
     jobs[t] = jb;
     if (n_threads == 1)
       worker(&jobs[t]);
@@ -681,7 +685,14 @@ int ORACLE_FN(run_closed_loop)(int model, int64_t n, const double* x0, const dou
   }
   if (n_threads > 1)
     for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  g_last_loop_seconds = 0.0;
+  for (int t = 0; t < n_threads; t++)
+    if (jobs[t].loop_seconds > g_last_loop_seconds) g_last_loop_seconds = jobs[t].loop_seconds;
   free(jobs);
   free(th);
   return 0;
 }
+
+/* max over the worker threads of the wall time spent inside the closed-loop step loops of the last
+ * run_closed_loop (controller construction, init_u0_newton and thread start-up excluded) */
+double ORACLE_FN(last_loop_seconds)(void) { return g_last_loop_seconds; }

@@ -94,6 +94,8 @@ int ORACLE_FN(run_closed_loop)(int model, int64_t n, const double* x0, const dou
                                double* x_traj, double* u_traj, double* x_fin, double* u_fin,
                                double* U_fin, double* dUdt_fin, int32_t* exit_hist,
                                double* ctl_seconds, int n_threads);
+/* max over worker threads of the wall time inside the step loops of the last run_closed_loop */
+double ORACLE_FN(last_loop_seconds)(void);
 
 #ifdef __cplusplus
 }

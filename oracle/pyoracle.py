@@ -73,6 +73,7 @@ class Oracle:
         f("run_closed_loop", C.c_int,
           [C.c_int, C.c_int64, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int,
            _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, C.c_int])
+        f("last_loop_seconds", C.c_double, [])
         if kind != "reference":
             f("sincos", None, [C.c_double, _dp, _dp])
 
@@ -139,6 +140,8 @@ class Oracle:
             out["exit_hist"].ctypes.data_as(_ip), _d(out["ctl_seconds"]), n_threads)
         if rc != 0:
             raise RuntimeError("run_closed_loop: bad arguments")
+        # wall time of the step loops alone (max over the worker threads): what a throughput figure should use
+        out["loop_seconds"] = float(self._last_loop_seconds())
         return out
 
 

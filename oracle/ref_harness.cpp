@@ -108,7 +108,9 @@ struct Job {
   int64_t n;
   const double *x0, *p, *u0;
   double *x_traj, *u_traj, *x_fin, *u_fin, *U_fin, *dUdt_fin, *ctl_seconds;
+  double* loop_seconds;  // [n_threads]: wall time each thread spent inside its closed-loop step loops
 };
+double g_last_loop_seconds = 0.0;
 
 template <class Model, class Sim>
 void run_slice(const Job& jb, int tid, int nth) {
@@ -130,6 +132,7 @@ void run_slice(const Job& jb, int tid, int nth) {
     ctl.init_u0(u);
     ctl.init_u0_newton(u, x, p0, jb.newton_iters);
     double acc = 0.0;
+    const double loop0 = now_s();
     for (int s = 0; s < jb.n_steps; s++) {
       const double t0 = now_s();
       ctl.control(u, x);
@@ -141,6 +144,7 @@ void run_slice(const Job& jb, int tid, int nth) {
         if (jb.u_traj) memcpy(jb.u_traj + (r * jb.n + n) * nu, u, sizeof(double) * nu);
       }
     }
+    if (jb.loop_seconds) jb.loop_seconds[tid] += now_s() - loop0;
     if (jb.x_fin) memcpy(jb.x_fin + (size_t)nx * n, x, sizeof(double) * nx);
     if (jb.u_fin) memcpy(jb.u_fin + (size_t)nu * n, u, sizeof(double) * nu);
     if (jb.U_fin) memcpy(jb.U_fin + (size_t)L * n, ctl.c.U, sizeof(double) * L);
@@ -237,8 +241,9 @@ int ref_run_closed_loop(int model, int64_t n, const double* x0, const double* p,
   if (ref_model_dims(model, dims) != 0 || n < 0 || !x0 || !u0 || (dims[2] > 0 && !p) || n_steps < 0) return -1;
   if (exit_hist) memset(exit_hist, 0xff, sizeof(int32_t) * 4 * (size_t)n);  // -1: not available
   if (n_threads < 1) n_threads = 1;
+  std::vector<double> loop_s((size_t)n_threads, 0.0);
   Job jb{model, p_full, newton_iters, n_steps, rec_stride, n, x0, p, u0,
-         x_traj, u_traj, x_fin, u_fin, U_fin, dUdt_fin, ctl_seconds};
+         x_traj, u_traj, x_fin, u_fin, U_fin, dUdt_fin, ctl_seconds, loop_s.data()};
   if (n_threads == 1) {
     run_slice_any(jb, 0, 1);
   } else {
@@ -246,7 +251,13 @@ int ref_run_closed_loop(int model, int64_t n, const double* x0, const double* p,
     for (int t = 0; t < n_threads; t++) th.emplace_back(run_slice_any, std::cref(jb), t, n_threads);
     for (auto& t : th) t.join();
   }
+  g_last_loop_seconds = 0.0;
+  for (double v : loop_s) g_last_loop_seconds = v > g_last_loop_seconds ? v : g_last_loop_seconds;
   return 0;
 }
+
+// max over the worker threads of the wall time spent inside the closed-loop step loops of the last
+// run_closed_loop (controller construction, init_u0_newton and thread start-up excluded)
+double ref_last_loop_seconds(void) { return g_last_loop_seconds; }
 
 }  // extern "C"
