@@ -42,6 +42,7 @@ SIGNATURES = {
     "cgmres_b200_get_x": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_get_u": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_step_closed_loop": (C.c_int, [_h, C.c_int]),
+    "cgmres_b200_step_closed_loop_log": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_void_p]),
     "cgmres_b200_set_t": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_get_t": (C.c_int, [_h, C.c_void_p]),
     "cgmres_b200_set_plant_integrator": (C.c_int, [_h, C.c_int]),

@@ -133,7 +133,13 @@ class BatchedCgmres:
 
     def control(self, x, out=None):
         x = _f64(x, (self.n, self.dim_x))
-        u = out if out is not None else np.empty((self.n, self.dim_u))
+        if out is None:
+            u = np.empty((self.n, self.dim_u))
+        else:  # the C ABI writes n*dim_u doubles straight into this buffer
+            u = out
+            if not (isinstance(u, np.ndarray) and u.dtype == np.float64 and u.flags.c_contiguous
+                    and u.flags.writeable and u.shape == (self.n, self.dim_u)):
+                raise ValueError(f"out must be a writable C-contiguous float64 array of shape ({self.n}, {self.dim_u})")
         check(lib().cgmres_b200_control(self._h, _ptr(u), _ptr(x)))
         return u
 
@@ -161,6 +167,14 @@ class BatchedCgmres:
 
     def step_closed_loop(self, n_steps: int = 1):
         check(lib().cgmres_b200_step_closed_loop(self._h, int(n_steps)))
+
+    def step_closed_loop_log(self, n_steps: int):
+        """n_steps closed-loop steps with the trajectory recorded on the device: returns
+        (x_log[n_steps][n][dim_x], u_log[n_steps][n][dim_u]) -- the rows the reference's mains print per step."""
+        xl = np.empty((int(n_steps), self.n, self.dim_x))
+        ul = np.empty((int(n_steps), self.n, self.dim_u))
+        check(lib().cgmres_b200_step_closed_loop_log(self._h, int(n_steps), _ptr(xl), _ptr(ul)))
+        return xl, ul
 
     def set_t(self, t):
         """Per-instance controller clocks t[n] (None: back to the batch-uniform clock)."""

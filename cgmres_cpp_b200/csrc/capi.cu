@@ -4,6 +4,7 @@
 // step with the host libm so that it is bit-identical to the reference's.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <omp.h>
@@ -11,6 +12,7 @@
 #include <atomic>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "cgmres_b200.h"
 #include "cgmres_b200/models.hpp"
@@ -77,6 +79,9 @@ static int sm_count_of(int device) {
 struct cgmres_b200_controller {
   int model = 0, mode = 0, device = 0;
   int64_t n = 0, ld = 0;
+  // set when a multi-stream control() failed half way: part of the batch may be one step ahead of the rest, so
+  // every later call on the handle is refused (destroy still works)
+  bool failed = false;
   const ModelInfo* mi = nullptr;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   // pipelined host-buffer control(): slices of the batch on side streams so that one slice's PCIe copies overlap
@@ -96,8 +101,20 @@ struct cgmres_b200_controller {
   size_t scratch_region = 0;       // doubles per region
   double* stage = nullptr;  // instance-major staging, grown on demand
   size_t stage_doubles = 0;
+  // third-generation persistent kernel (pipe2_update.cuh) behind MODE_FAST / MODE_PIPELINED_EXACT; generation 2
+  // (pipe_update.cuh) stays reachable for A/B runs with CGMRES_B200_PIPE_GEN=2 in the environment at create time
+  int pipe_gen = 3;
+  static constexpr int kMaxFusedSteps = 256;  // closed-loop steps per multi-step launch (horizon-ramp table rows)
+  double* dtau_tab = nullptr;                 // [2][kMaxFusedSteps][2] device table, double-buffered across launches
+  int dtau_tab_next = 0;
+  double *x_log = nullptr, *u_log = nullptr;  // device trajectory log of step_closed_loop_log, grown on demand
+  size_t log_steps = 0;
 
-  bool soa() const { return mode == CGMRES_B200_MODE_EXACT; }  // exact: [element][instance]; on-chip kernels: [instance][element]
+  bool soa() const { return mode == CGMRES_B200_MODE_EXACT; }
+  // the modes whose kernel advances several steps of the same instances per launch
+  bool fused_steps() const {
+    return pipe_gen == 3 && (mode == CGMRES_B200_MODE_FAST || mode == CGMRES_B200_MODE_PIPELINED_EXACT);
+  }  // exact: [element][instance]; on-chip kernels: [instance][element]
   int L() const { return mi->L(); }
   int ptau_rows_full() const { return (mi->dv + 1) * mi->dim_p; }
 
@@ -138,6 +155,11 @@ struct cgmres_b200_controller {
       scratch_region = (mode == CGMRES_B200_MODE_FAST)              ? fast_scratch_doubles(model, device, n)
                        : (mode == CGMRES_B200_MODE_PIPELINED_EXACT) ? pipelined_exact_scratch_doubles(model, device, n)
                                                                     : 0;
+      if (fused_steps()) {
+        const size_t s3 = pipe2_scratch_doubles(model, device, n);
+        scratch_region = s3 > scratch_region ? s3 : scratch_region;
+        if ((rc = dalloc(&dtau_tab, (size_t)2 * kMaxFusedSteps * 2))) return rc;
+      }
       if (scratch_region && (rc = dalloc(&scratch, scratch_region * (size_t)(kSlices + 1)))) return rc;
       if ((rc = ensure_stage((size_t)n * (size_t)(mi->dim_x + mi->dim_u + mi->dim_p + 1)))) return rc;
       return 0;
@@ -169,6 +191,9 @@ struct cgmres_b200_controller {
     cudaFree(dbg);
     cudaFree(scratch);
     cudaFree(stage);
+    cudaFree(dtau_tab);
+    cudaFree(x_log);
+    cudaFree(u_log);
     for (int i = 0; i < kSlices; i++) {
       if (side[i]) cudaStreamDestroy(side[i]);
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
@@ -188,8 +213,13 @@ struct cgmres_b200_controller {
   }
 
   // on-chip modes: one update of instances [lo, lo+cnt) on stream s (pointer offsets into the instance-major state)
-  int launch_slice(int64_t lo, int64_t cnt, int plant, double dt_t, double dt_th, cudaStream_t s, int region = 0) {
+  int launch_slice(int64_t lo, int64_t cnt, int plant, double dt_t, double dt_th, cudaStream_t s, int region = 0,
+                   int n_steps = 1, const double* tab = nullptr, double* xl = nullptr, double* ul = nullptr) {
     FastArgs f;
+    f.n_steps = n_steps;
+    f.dtau_tab = tab;
+    f.x_log = xl;
+    f.u_log = ul;
     const int64_t prow = ptau_full ? (int64_t)ptau_rows_full() : (int64_t)mi->dim_p;
     f.n = cnt;
     f.x = x + lo * mi->dim_x;
@@ -204,13 +234,57 @@ struct cgmres_b200_controller {
     f.plant = plant;
     f.dbg = dbg;
     f.scratch = scratch ? scratch + scratch_region * (size_t)region : nullptr;
-    if (mode == CGMRES_B200_MODE_FAST)
-      CU(fast_launch_control(model, ptau_full, f, s));
-    else if (mode == CGMRES_B200_MODE_PIPELINED_EXACT)
-      CU(pipelined_exact_launch_control(model, ptau_full, f, s));
-    else
+    if (mode == CGMRES_B200_MODE_FAST) {
+      // small single-step batches: the first-generation kernel's dependent chain per update is the shortest
+      const bool big = cnt > (int64_t)onchip_exact_instances_per_cta(model) * sm_count_of(device);
+      if (pipe_gen == 3 && (big || n_steps > 1 || xl || ul))
+        CU(pipe2_fast_launch_control(model, ptau_full, f, s));
+      else
+        CU(fast_launch_control(model, ptau_full, f, s));
+    } else if (mode == CGMRES_B200_MODE_PIPELINED_EXACT) {
+      if (pipe_gen == 3)
+        CU(pipe2_exact_launch_control(model, ptau_full, f, s));
+      else
+        CU(pipelined_exact_launch_control(model, ptau_full, f, s));
+    } else {
       CU(onchip_exact_launch_control(model, ptau_full, f, s));
+    }
     g_launches++;
+    return 0;
+  }
+
+  // n_steps closed-loop steps of the whole batch in ONE launch of the third-generation kernel (fused_steps() modes):
+  // the horizon ramps of every step are evaluated here with the host libm, exactly like the per-step path
+  int launch_fused(int n_steps, int plant, double* xl, double* ul) {
+    if (n_steps <= 0 || n == 0) return 0;
+    std::vector<double> tab((size_t)2 * n_steps);
+    double tt = t;
+    for (int s = 0; s < n_steps; s++) {
+      tab[2 * s] = dtau(tt);
+      tab[2 * s + 1] = dtau(tt + mi->h);
+      tt = tt + mi->dt;  // cgmres.hpp:107 (accumulated, not i*dt)
+    }
+    double* dtab = dtau_tab + (size_t)dtau_tab_next * kMaxFusedSteps * 2;
+    dtau_tab_next ^= 1;
+    CU(cudaMemcpyAsync(dtab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, stream));
+    int rc = launch_slice(0, n, plant, tab[0], tab[1], stream, 0, n_steps, dtab, xl, ul);
+    if (rc) return rc;
+    t = tt;
+    return 0;
+  }
+
+  int ensure_log(size_t steps) {
+    if (steps <= log_steps) return 0;
+    if (x_log) {
+      CU(cudaStreamSynchronize(stream));
+      CU(cudaFree(x_log));
+      CU(cudaFree(u_log));
+      x_log = u_log = nullptr;
+      log_steps = 0;
+    }
+    CU(cudaMalloc(&x_log, sizeof(double) * steps * (size_t)(n ? n : 1) * mi->dim_x));
+    CU(cudaMalloc(&u_log, sizeof(double) * steps * (size_t)(n ? n : 1) * mi->dim_u));
+    log_steps = steps;
     return 0;
   }
 
@@ -279,8 +353,10 @@ struct cgmres_b200_controller {
   }
 };
 
-#define CHECK_H(h) \
-  if (!(h)) return fail(CGMRES_B200_EINVAL, "null handle")
+#define CHECK_H(h)                                               \
+  if (!(h)) return fail(CGMRES_B200_EINVAL, "null handle");      \
+  if ((h)->failed)                                               \
+  return fail(CGMRES_B200_ECUDA, "handle is unusable: an earlier sliced control() failed part way (destroy it)")
 #define ON_DEVICE(h) CU(cudaSetDevice((h)->device))
 
 template <class Sim>
@@ -361,6 +437,7 @@ int cgmres_b200_create(int model, int64_t n, int device, int mode, cgmres_b200_h
   h->ld = (n + 31) & ~(int64_t)31;
   if (h->ld == 0) h->ld = 32;
   h->mi = mi;
+  if (const char* gen = getenv("CGMRES_B200_PIPE_GEN")) h->pipe_gen = (atoi(gen) == 2) ? 2 : 3;
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete h;
@@ -506,7 +583,8 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
   if (!h->soa()) {  // instance-major state == ABI layout: x straight into place, u straight out
     if (n == 0) return 0;
     // slices are whole "waves" (the instances all SMs hold at once) so that no slice ends in a partly filled wave
-    const int64_t wave = (int64_t)onchip_instances_per_cta(h->model, h->mode) * sm_count_of(h->device);
+    const int per_cta = h->fused_steps() ? pipe2_instances_per_cta(h->model) : onchip_instances_per_cta(h->model, h->mode);
+    const int64_t wave = (int64_t)per_cta * sm_count_of(h->device);
     const int64_t waves = (h->n + wave - 1) / wave;
     const int S = (h->n >= 8192 && waves >= 2)
                       ? (int)(waves < cgmres_b200_controller::kSlices ? waves : cgmres_b200_controller::kSlices)
@@ -535,21 +613,34 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
     } else {
       for (int i = 0; i <= S; i++) wb[i] = waves * i / S;
     }
+    // anything that fails inside the loop leaves earlier slices already running: drain them and poison the handle
+    auto abandon = [&](int enqueued, int rc_) {
+      for (int k = 0; k < enqueued; k++) cudaStreamSynchronize(h->side[k]);
+      h->failed = true;
+      return rc_;
+    };
+#define CU_SLICE(call)                                                     \
+  do {                                                                     \
+    cudaError_t e_ = (call);                                               \
+    if (e_ != cudaSuccess) return abandon(i + 1, cuda_fail(e_, #call));    \
+  } while (0)
     for (int i = 0; i < S; i++) {
       const int64_t lo = wb[i] * wave;
       const int64_t hi_ = wb[i + 1] * wave;
       const int64_t hi = hi_ < h->n ? hi_ : h->n;
       const int64_t cnt = hi - lo;
       cudaStream_t st = h->side[i];
-      CU(cudaStreamWaitEvent(st, h->ev_begin, 0));
-      CU(cudaMemcpyAsync(h->x + lo * nx, x + lo * nx, sizeof(double) * (size_t)cnt * nx, cudaMemcpyHostToDevice, st));
+      CU_SLICE(cudaStreamWaitEvent(st, h->ev_begin, 0));
+      CU_SLICE(cudaMemcpyAsync(h->x + lo * nx, x + lo * nx, sizeof(double) * (size_t)cnt * nx, cudaMemcpyHostToDevice,
+                               st));
       int rcu = h->launch_slice(lo, cnt, 0, dt_t, dt_th, st, 1 + i);
-      if (rcu) return rcu;
-      CU(cudaMemcpyAsync(u + lo * nu, h->u_out + lo * nu, sizeof(double) * (size_t)cnt * nu, cudaMemcpyDeviceToHost,
-                         st));
-      CU(cudaEventRecord(h->ev_done[i], st));
-      CU(cudaStreamWaitEvent(h->stream, h->ev_done[i], 0));  // later work on the handle's stream sees the slices
+      if (rcu) return abandon(i + 1, rcu);
+      CU_SLICE(cudaMemcpyAsync(u + lo * nu, h->u_out + lo * nu, sizeof(double) * (size_t)cnt * nu,
+                               cudaMemcpyDeviceToHost, st));
+      CU_SLICE(cudaEventRecord(h->ev_done[i], st));
+      CU_SLICE(cudaStreamWaitEvent(h->stream, h->ev_done[i], 0));  // later work on the handle's stream sees the slices
     }
+#undef CU_SLICE
     h->t = h->t + h->mi->dt;
     for (int i = 0; i < S; i++) CU(cudaEventSynchronize(h->ev_done[i]));
     return 0;
@@ -592,10 +683,66 @@ int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps) {
   CHECK_H(h);
   ON_DEVICE(h);
   if (n_steps < 0) return fail(CGMRES_B200_EINVAL, "negative step count");
+  if (h->fused_steps() && n_steps > 1) {  // the same resident instances advance several steps per launch
+    for (int done = 0; done < n_steps;) {
+      const int chunk = (n_steps - done) < cgmres_b200_controller::kMaxFusedSteps
+                            ? (n_steps - done)
+                            : cgmres_b200_controller::kMaxFusedSteps;
+      int rc = h->launch_fused(chunk, h->integrator, nullptr, nullptr);
+      if (rc) return rc;
+      done += chunk;
+    }
+    return 0;
+  }
   for (int s = 0; s < n_steps; s++) {
     int rc = h->launch_update(h->integrator);
     if (rc) return rc;
   }
+  return 0;
+}
+
+int cgmres_b200_step_closed_loop_log(cgmres_b200_handle h, int n_steps, double* x_log, double* u_log) {
+  CHECK_H(h);
+  ON_DEVICE(h);
+  if (n_steps < 0 || (n_steps > 0 && (!x_log || !u_log))) return fail(CGMRES_B200_EINVAL, "bad log arguments");
+  const size_t n = (size_t)h->n;
+  if (n == 0 || n_steps == 0) return 0;
+  const int nx = h->mi->dim_x, nu = h->mi->dim_u;
+  // chunks of the trajectory stay on the device until the chunk is complete (at most ~64 MB of log per chunk)
+  size_t per_step = n * (size_t)(nx + nu) * sizeof(double);
+  int chunk_max = (int)((size_t)(64u << 20) / (per_step ? per_step : 1));
+  if (chunk_max < 1) chunk_max = 1;
+  if (chunk_max > cgmres_b200_controller::kMaxFusedSteps) chunk_max = cgmres_b200_controller::kMaxFusedSteps;
+  for (int done = 0; done < n_steps;) {
+    const int chunk = (n_steps - done) < chunk_max ? (n_steps - done) : chunk_max;
+    int rc = h->ensure_log((size_t)chunk);
+    if (rc) return rc;
+    if (h->fused_steps()) {
+      rc = h->launch_fused(chunk, h->integrator, h->x_log, h->u_log);
+      if (rc) return rc;
+    } else {  // one launch per step; the step's x and u are appended to the device log by stream-ordered copies
+      for (int s = 0; s < chunk; s++) {
+        rc = h->launch_update(h->integrator);
+        if (rc) return rc;
+        if (h->soa()) {
+          CU(launch_soa_to_aos(h->x, h->x_log + (size_t)s * n * nx, h->n, nx, h->ld, h->stream));
+          CU(launch_soa_to_aos(h->u_out, h->u_log + (size_t)s * n * nu, h->n, nu, h->ld, h->stream));
+          g_launches += 2;
+        } else {
+          CU(cudaMemcpyAsync(h->x_log + (size_t)s * n * nx, h->x, sizeof(double) * n * nx, cudaMemcpyDeviceToDevice,
+                             h->stream));
+          CU(cudaMemcpyAsync(h->u_log + (size_t)s * n * nu, h->u_out, sizeof(double) * n * nu,
+                             cudaMemcpyDeviceToDevice, h->stream));
+        }
+      }
+    }
+    CU(cudaMemcpyAsync(x_log + (size_t)done * n * nx, h->x_log, sizeof(double) * (size_t)chunk * n * nx,
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(u_log + (size_t)done * n * nu, h->u_log, sizeof(double) * (size_t)chunk * n * nu,
+                       cudaMemcpyDeviceToHost, h->stream));
+    done += chunk;
+  }
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -56,6 +56,11 @@ struct FastArgs {
   long long* dbg;      // phase timestamps (debug builds with -DCG_FAST_TIMING), else unused / null
   double* scratch;     // pipelined fast kernel: per-CTA spill area (fast_scratch_doubles()), one region per
                        // concurrently running launch; unused by the other on-chip kernels
+  // third-generation kernel (pipe2_update.cuh) only; the other kernels advance exactly one step per launch:
+  int n_steps = 1;                   // closed-loop steps of the same resident instances inside this launch
+  const double* dtau_tab = nullptr;  // n_steps > 1, lock step: {get_dtau(t_s), get_dtau(t_s + h)} per step, host-evaluated
+  double* x_log = nullptr;           // optional trajectory log [n_steps][n][dim_x] (x after each plant step)
+  double* u_log = nullptr;           // optional [n_steps][n][dim_u] (u returned by each control update)
 };
 
 // on-chip kernels: fast_kernels.cu (FMA, shuffle reductions) and their sequential-sum, no-FMA twin compiled in
@@ -64,6 +69,11 @@ cudaError_t fast_launch_control(int model, bool ptau_full, const FastArgs& a, cu
 cudaError_t onchip_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 // the fast mode's persistent pipelined kernel built with sequential sums and no FMA (onchip_exact_kernels.cu)
 cudaError_t pipelined_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
+// third generation (pipe2_update.cuh): FMA build (pipe2_fast_kernels.cu) and bit-exact build (pipe2_exact_kernels.cu)
+cudaError_t pipe2_fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
+cudaError_t pipe2_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
+size_t pipe2_scratch_doubles(int model, int device, int64_t n);
+int pipe2_instances_per_cta(int model);
 int fast_instances_per_cta(int model);
 int onchip_exact_instances_per_cta(int model);
 inline int onchip_instances_per_cta(int model, int mode) {  // mode 1 = fast, 2 = onchip_exact, 3 = pipelined exact

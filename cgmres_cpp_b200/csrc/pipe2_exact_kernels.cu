@@ -1,0 +1,21 @@
+// pipe2_exact_kernels.cu -- the third-generation persistent kernel (pipe2_update.cuh) built bit-exact: compiled
+// WITHOUT FMA contraction (-fmad=false), EXACT = true (the reference's operation order; its 21 sequential sums per
+// update run lane-per-instance on the serial warps).  Serves MODE_PIPELINED_EXACT.
+#ifndef CG_SWEEP_UNROLL
+#define CG_SWEEP_UNROLL 10
+#endif
+#include "pipe2_launch.cuh"
+
+namespace cgmres_b200 {
+
+cudaError_t pipe2_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s) {
+  switch (model) {
+    case MODEL_MSD: return pipe2::launch<MassSpringDamperModel, MassSpringDamperSimulator, true>(ptau_full, a, s);
+    case MODEL_ARM: return pipe2::launch<ArmPendulumModel, ArmPendulumSimulator, true>(ptau_full, a, s);
+    case MODEL_SEMIACTIVE:
+      return pipe2::launch<SemiactiveDamperModel, SemiactiveDamperSimulator, true>(ptau_full, a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace cgmres_b200

@@ -137,6 +137,10 @@ class Cgmres : public Gmres {
   void step_closed_loop(int n_steps) {
     cgmres_b200::check(cgmres_b200_step_closed_loop(h_, n_steps), "step_closed_loop");
   }
+  // the same with the trajectory recorded on the device: x_log[n_steps][n][dim_x], u_log[n_steps][n][dim_u]
+  void step_closed_loop_log(int n_steps, double* x_log, double* u_log) {
+    cgmres_b200::check(cgmres_b200_step_closed_loop_log(h_, n_steps, x_log, u_log), "step_closed_loop_log");
+  }
   // per-instance controller clocks t[n] (nullptr: back to the batch-uniform clock)
   void set_t(const double* t) { cgmres_b200::check(cgmres_b200_set_t(h_, t), "set_t"); }
   void get_t(double* t) const { cgmres_b200::check(cgmres_b200_get_t(h_, t), "get_t"); }

@@ -121,6 +121,15 @@ int cgmres_b200_get_u(cgmres_b200_handle h, double* u);
 /* n_steps x { control(u,x); x += Simulator::dxdt(x,u)*dt } entirely on the device: the loop body of
  * <example>/main.cpp:66-77 (forward Euler).  Asynchronous on the handle's stream. */
 int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps);
+/* (MODE_FAST / MODE_PIPELINED_EXACT run n_steps > 1 as multi-step launches of the persistent kernel: the same resident
+ *  instances advance up to 256 steps per launch, per-step horizon ramps from a host-evaluated table.  Results are the
+ *  ones of n_steps single-step calls, bit for bit.) */
+
+/* The same loop with the trajectory recorded ON THE DEVICE and copied out chunk-wise: x_log[n_steps][n][dim_x] = the
+ * plant state after every step, u_log[n_steps][n][dim_u] = the input every control update returned -- the rows the
+ * reference's mains fprintf() to <example>_{x,u}.txt (mass_spring_damper/main.cpp:78-87), without a host round trip
+ * per step.  Host arrays; returns when they are complete. */
+int cgmres_b200_step_closed_loop_log(cgmres_b200_handle h, int n_steps, double* x_log, double* u_log);
 
 /* Per-instance controller clocks (controllers started at different times): t[n] host.  From then on
  * every instance evaluates its own horizon step get_dtau(t_i), get_dtau(t_i + h) on the device (CUDA exp: within

@@ -138,7 +138,38 @@ def test_unmodified_main_on_the_gpu_reproduces_the_reference_output_files(built,
         arm_file = example == "arm_type_inverted_pendulum" or name.endswith(("x2.txt", "u2.txt"))
         if not arm_file:
             assert a == b, f"{name}: not byte-identical to the reference program's output"
-        else:  # sin/cos: portable (ours) vs glibc (reference) differ in the last bit; %f prints 6 decimals
+        else:
+            # The reference calls libm sin/cos; the device uses the portable pair (<= 1 ulp apart)
+            # and the swing-up amplifies that last-bit difference to ~3e-3 in mid-run before both settle on the same
+            # equilibrium.  So: (a) the first 1000 steps agree with the reference program to the printed precision,
+            # (b) the last row (settled) agrees, (c) the WHOLE file is byte-identical to the C oracle built with the
+            # same portable sin/cos, formatted like main.cpp:78-87.
             ta, tb = _table(d_ours / name), _table(d_ref / name)
             assert ta.shape == tb.shape
-            assert np.abs(ta - tb).max() <= 5e-6, (name, float(np.abs(ta - tb).max()))
+            assert np.abs(ta[:1000] - tb[:1000]).max() <= 2e-6, (name, float(np.abs(ta[:1000] - tb[:1000]).max()))
+            assert np.abs(ta[-1] - tb[-1]).max() <= 2e-6
+            assert a == _arm_oracle_text(name.split("_")[-1][0]), f"{name}: differs from the portable-trig oracle"
+
+
+_ARM_TEXT = {}
+
+
+def _arm_oracle_text(which: str) -> bytes:
+    """<arm>_x.txt / _u.txt as main.cpp writes them (arm_type_inverted_pendulum/main.cpp:59-84), from the C oracle
+    built with the device's portable sin/cos."""
+    if not _ARM_TEXT:
+        from cgmres_cpp_b200 import workloads
+        from oracle import pyoracle as po
+
+        ora = po.load("port_ptrig")
+        ic = workloads.SHIPPED[po.ARM]
+        steps = ic["steps"]
+        out = ora.run_closed_loop(po.ARM, np.array([ic["x0"]]), np.array([ic["p"]]), np.array(ic["u0"]), steps,
+                                  rec_stride=1)
+        dt = ora.params(po.ARM)["dt"]
+        for key, traj in (("x", out["x_traj"][:, 0, :]), ("u", out["u_traj"][:, 0, :])):
+            lines = []
+            for i in range(steps):
+                lines.append("%f" % (dt * i) + "".join("\t%f" % v for v in traj[i]) + "\n")
+            _ARM_TEXT[key] = "".join(lines).encode()
+    return _ARM_TEXT[which]
