@@ -10,7 +10,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcgmres_b200.so")
+# (CGMRES_B200_LIB: load an instrumented build of the same library instead, e.g. the -DCG_PIPE_TIMING one of
+#  tools/pipe_wait_times.py; a debugging knob, not a fallback)
+LIB_PATH = os.environ.get("CGMRES_B200_LIB") or os.path.join(_HERE, "libcgmres_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -11,9 +11,11 @@ namespace cgmres_b200 {
 cudaError_t pipe2_fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s) {
   switch (model) {
     case MODEL_MSD: return pipe2::launch<MassSpringDamperModel, MassSpringDamperSimulator, false>(ptau_full, a, s);
+#ifndef CG_ONLY_MSD  // (tuning builds instantiate the msd kernels only: tools/quick_msd_build.sh)
     case MODEL_ARM: return pipe2::launch<ArmPendulumModel, ArmPendulumSimulator, false>(ptau_full, a, s);
     case MODEL_SEMIACTIVE:
       return pipe2::launch<SemiactiveDamperModel, SemiactiveDamperSimulator, false>(ptau_full, a, s);
+#endif
   }
   return cudaErrorInvalidValue;
 }

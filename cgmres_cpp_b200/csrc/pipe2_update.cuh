@@ -27,6 +27,8 @@
 // Arithmetic: EXACT = false: FMA contraction + butterfly sums (tolerance parity); EXACT = true (instantiated only in
 // the -fmad=false translation unit): the reference's operation order and sequential sums, bit-identical results.
 #pragma once
+#include <type_traits>
+
 #include "pipe_update.cuh"
 
 namespace cgmres_b200 {
@@ -167,7 +169,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   auto BL = [](int g) { return 1 + NG + g; };
   double* const scr_cta = a.scratch + (size_t)blockIdx.x * Y::scratch_doubles_per_cta;
 #ifdef CG_PIPE_TIMING
-  long long t_wait = 0, t_sw = 0, t_sum = 0, t_vwork = 0;
+  long long t_wait = 0, t_sw = 0, t_sum = 0, t_dh = 0, t_fin = 0, t_si = 0, t_lap = 0;
+  (void)t_lap;
   const long long t_begin = clock64();
 #endif
 
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
     };
     // stage-parallel dHdu (cgmres.hpp:156-161), one stage per lane; F_i overwrites u_i in X
     auto stage_dhdu = [&](double* blk, const double* sc, const double* x0, int64_t n) {
+      CG_PIPE_WORK_BEGIN;
       const double* pf = PFULL ? a.ptau + n * prow : nullptr;
       for (int i = lane; i < M::dv; i += 32) {
         double xi[nx], u[nu], p[Y::np1], lm[nx], hu[nu];
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         for (int j = 0; j < nu; j++) blk[Y::oX + i * nu + j] = hu[j];
       }
       __syncwarp();
+      CG_PIPE_WORK_END(t_dh);
     };
 
     // ---- final update of (round r, group g, global step index gs): back substitution (gmres.hpp:100-107),
@@ -399,10 +404,20 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
       double* blk = blk_of(g);
       double* sc = blk + Y::oS;
       const double* __restrict__ Ug = a.U + n * (int64_t)L;
+      if (step == 0) {
 #pragma unroll
-      for (int q = 0; q < Q; q++) {  // global -> shared without a register round trip; waited for below
-        const int j = lane + 32 * q;
-        if (j < L) cp_async8(blk + Y::oX + j, Ug + j);
+        for (int q = 0; q < Q; q++) {  // global -> shared without a register round trip; waited for below
+          const int j = lane + 32 * q;
+          if (j < L) cp_async8(blk + Y::oX + j, Ug + j);
+        }
+      } else {  // same instances, next step: this lane wrote these elements a moment ago (plain loads see them)
+        double uu[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          const int j = lane + 32 * q;
+          uu[q] = (j < L) ? Ug[j] : 0.0;
+        }
+        sm_put(blk + Y::oX, uu);
       }
       {  // dUdt is first needed two sweeps from now: pull its lines into L2 meanwhile (no registers held)
         const char* dline = reinterpret_cast<const char*>(a.dUdt + n * (int64_t)L) + 128 * lane;
@@ -570,17 +585,17 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
       if (n < a.n && lane < nx) sc[Y::sXO + lane] = sc[Y::sX + lane];
       __syncwarp();
       if (step + 1 < n_steps) {  // same instances, next closed-loop step: the new U / x go out and come straight back
-        final_update(r, g, step);
-        state_in(r, g, step + 1);
+        { CG_PIPE_WORK_BEGIN; final_update(r, g, step); CG_PIPE_WORK_END(t_fin); }
+        { CG_PIPE_WORK_BEGIN; state_in(r, g, step + 1); CG_PIPE_WORK_END(t_si); }
         bar_arrive(BX(g), T);
         return false;
       }
       if (more_rounds) {  // next round's state first, so that the serial warp never waits for a round to drain
-        state_in(r + gridDim.x, g, 0);
+        { CG_PIPE_WORK_BEGIN; state_in(r + gridDim.x, g, 0); CG_PIPE_WORK_END(t_si); }
         bar_arrive(BX(g), T);
         return true;
       }
-      final_update(r, g, step);
+      { CG_PIPE_WORK_BEGIN; final_update(r, g, step); CG_PIPE_WORK_END(t_fin); }
       return false;
     };
 
@@ -602,7 +617,11 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           const int64_t n = r * NI + (int64_t)g * GI + vw;
           const bool has = n < a.n;
           double* blk = blk_of(g);
-          if (owed && step == 0) final_update(r - gridDim.x, g, n_steps - 1);  // overlaps the serial warp's sweep
+          if (owed && step == 0) {  // overlaps the serial warp's sweep
+            CG_PIPE_WORK_BEGIN;
+            final_update(r - gridDim.x, g, n_steps - 1);
+            CG_PIPE_WORK_END(t_fin);
+          }
           { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
           if (has) {
             const double* __restrict__ Ug = a.U + n * (int64_t)L;
@@ -858,6 +877,11 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
     if (wid == 0) {
       a.dbg[48] = t_sw;
       a.dbg[49] = t_sum;
+    }
+    if (wid == 1) {
+      a.dbg[51] = t_dh;
+      a.dbg[52] = t_fin;
+      a.dbg[53] = t_si;
     }
   }
 #endif

@@ -14,8 +14,9 @@ from cgmres_cpp_b200 import workloads as po  # noqa: E402
 
 model = {"msd": 0, "arm": 1, "semiactive": 2}[sys.argv[1] if len(sys.argv) > 1 else "msd"]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+mode = {"fast": cg.MODE_FAST, "pipelined_exact": cg.MODE_PIPELINED_EXACT}[sys.argv[3] if len(sys.argv) > 3 else "fast"]
 x0, p, u0 = po.synthetic_batch(model, n)
-c = cg.BatchedCgmres(model, n, mode=cg.MODE_FAST)
+c = cg.BatchedCgmres(model, n, mode=mode)
 if p is not None:
     c.set_ptau_repeat(p)
 c.init_u0(u0); c.init_u0_newton(u0, x0, p, 10); c.set_x(x0)
@@ -28,6 +29,10 @@ for w in range(24):
     if t[2 * w + 1]:
         role = "serial" if w == 0 else "vector"
         print(f"warp {w:2d} ({role}): total {t[2*w+1]:8d} cycles, blocked at barriers {t[2*w]:8d} = {100.0*t[2*w]/t[2*w+1]:.1f} %")
+if os.environ.get("CGMRES_B200_PIPE_GEN") != "2":
+    print(f"serial warp 0: inside sweeps {t[48]} cycles, inside sequential sums {t[49]} (sum over its rounds)")
+    print(f"vector warp 0 (warp 1): stage-parallel dHdu {t[51]}, final updates {t[52]}, state in {t[53]}")
+    sys.exit(0)
 if t[48]:
     print(f"serial warp 0: first pass {t[48]} cycles, second pass {t[49]}, Arnoldi sweeps {t[50]} (sum over its rounds)")
 if t[51] or t[54]:
