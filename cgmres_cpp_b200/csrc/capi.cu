@@ -156,7 +156,7 @@ struct cgmres_b200_controller {
                        : (mode == CGMRES_B200_MODE_PIPELINED_EXACT) ? pipelined_exact_scratch_doubles(model, device, n)
                                                                     : 0;
       if (fused_steps()) {
-        const size_t s3 = pipe2_scratch_doubles(model, device, n);
+        const size_t s3 = pipe2_scratch_doubles(model, device, n, mode == CGMRES_B200_MODE_PIPELINED_EXACT);
         scratch_region = s3 > scratch_region ? s3 : scratch_region;
         if ((rc = dalloc(&dtau_tab, (size_t)2 * kMaxFusedSteps * 2))) return rc;
       }
@@ -583,7 +583,8 @@ int cgmres_b200_control(cgmres_b200_handle h, double* u, const double* x) {
   if (!h->soa()) {  // instance-major state == ABI layout: x straight into place, u straight out
     if (n == 0) return 0;
     // slices are whole "waves" (the instances all SMs hold at once) so that no slice ends in a partly filled wave
-    const int per_cta = h->fused_steps() ? pipe2_instances_per_cta(h->model) : onchip_instances_per_cta(h->model, h->mode);
+    const int per_cta = h->fused_steps() ? pipe2_instances_per_cta(h->model, h->mode == CGMRES_B200_MODE_PIPELINED_EXACT)
+                                          : onchip_instances_per_cta(h->model, h->mode);
     const int64_t wave = (int64_t)per_cta * sm_count_of(h->device);
     const int64_t waves = (h->n + wave - 1) / wave;
     const int S = (h->n >= 8192 && waves >= 2)

@@ -10,10 +10,9 @@
 #include "fast_update.cuh"
 #include "pipe_launch.cuh"
 
-// experiment knob (tools/sweep_build.sh): build the "fast" entry point with the reference's sequential sums
-#ifndef CG_FAST_SEQ_SUMS
-#define CG_FAST_SEQ_SUMS false
-#endif
+// (EXACT_SUMS = true instantiations of fast::control_kernel belong to onchip_exact_kernels.cu alone: that unit is
+//  compiled with -fmad=false, and two units instantiating the same specialisation with different floating-point
+//  flags would collide at link time and silently pick one.)
 
 // 1: the persistent warp-specialised kernel (pipe_update.cuh) serves the fast mode; 0: the first-generation
 // one-round-per-CTA kernel (fast_update.cuh).  Per model: the pipelined kernel wins where the vector work and the
@@ -42,15 +41,15 @@ cudaError_t launch_t(bool pfull, const FastArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((a.n + Y::G - 1) / Y::G);
   cudaError_t e;
   if (pfull) {
-    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, true, CG_FAST_SEQ_SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Y::smem_bytes);
     if (e != cudaSuccess) return e;
-    fast::control_kernel<M, Sim, true, CG_FAST_SEQ_SUMS><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
+    fast::control_kernel<M, Sim, true, false><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
   } else {
-    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, false, CG_FAST_SEQ_SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(fast::control_kernel<M, Sim, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Y::smem_bytes);
     if (e != cudaSuccess) return e;
-    fast::control_kernel<M, Sim, false, CG_FAST_SEQ_SUMS><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
+    fast::control_kernel<M, Sim, false, false><<<grid, Y::threads, Y::smem_bytes, s>>>(a);
   }
   return cudaGetLastError();
 }

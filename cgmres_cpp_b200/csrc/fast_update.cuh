@@ -45,6 +45,12 @@ constexpr int kSmemBudget = 227 * 1024 - 1024;  // minus the per-CTA reserved ki
 #endif
 #define CG_PRAGMA(x) _Pragma(#x)
 #define CG_UNROLL(n) CG_PRAGMA(unroll n)
+// stages per unrolled body of a model's serial recursions: the translation unit's CG_SWEEP_UNROLL, halved for models
+// whose stage is register-hungry (the arm model's sin/cos: 10 stages deep spilled in the persistent kernels)
+template <class M>
+struct SweepUnroll {
+  static constexpr int value = (M::dim_x > 2 && M::dim_u < 4 && CG_SWEEP_UNROLL > 5) ? 5 : CG_SWEEP_UNROLL;
+};
 // phase timestamps of one warp of CTA 0 (debug builds only: -DCG_FAST_TIMING), read back by tools/phase_times.py
 #ifdef CG_FAST_TIMING
 #define CG_MARK(i)                                                                      \
@@ -281,7 +287,7 @@ __device__ __forceinline__ void lane_rollout(const double* __restrict__ in, doub
   for (int j = 0; j < np; j++) p[j] = pconst[j];  // constant reference (set_ptau_repeat); PFULL reloads per stage
 #pragma unroll
   for (int j = 0; j < nx; j++) xc[j] = x0[j];
-CG_UNROLL(CG_SWEEP_UNROLL)
+CG_UNROLL((SweepUnroll<M>::value))
   for (int i = 0; i < dv; i++) {
     double f[nx];
 #pragma unroll
@@ -305,11 +311,14 @@ CG_UNROLL(CG_SWEEP_UNROLL)
 
 // Full sweep with dHdu inside (used for the three Krylov-independent evaluations, where 3 lanes per instance
 // are busy): out[i] = dHdu(x_i, u_i, p_i, lambda_{i+1})   (cgmres.hpp:113-162)
+// share_mask != 0: several lanes of the warp read the SAME `in` while one of them writes `out == in` (the second
+// generation's dual-trajectory pass): the lanes of the mask then synchronise between a stage's loads and its stores,
+// so the reader never depends on lock-step execution to see u_i before it is overwritten.
 template <class M, bool PFULL, int SX>
 __device__ __forceinline__ void lane_sweep_full(const double* in, double* out, double* __restrict__ xt,
                                                 const double* __restrict__ x0, const double dtau,
                                                 const double* __restrict__ pconst,
-                                                const double* __restrict__ pfull) {
+                                                const double* __restrict__ pfull, const unsigned share_mask = 0u) {
   using Y = Lay<M>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, dv = Y::dv;
   double xc[nx], lmd[nx], u[nu], p[Y::np1];
@@ -321,7 +330,7 @@ __device__ __forceinline__ void lane_sweep_full(const double* in, double* out, d
     for (int j = 0; j < np; j++) p[j] = pfull[dv * np + j];
   }
   M::dPhidx(lmd, xc, p);  // cgmres.hpp:145
-CG_UNROLL(CG_SWEEP_UNROLL)
+CG_UNROLL((SweepUnroll<M>::value))
   for (int i = dv - 1; i >= 0; i--) {  // cgmres.hpp:146-161
     double xi[nx], hu[nu], hx[nx];
 #pragma unroll
@@ -333,6 +342,7 @@ CG_UNROLL(CG_SWEEP_UNROLL)
       for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
     }
     M::dHdu(hu, xi, u, p, lmd);
+    if (share_mask) __syncwarp(share_mask);  // every sharing lane holds u_i before stage i is overwritten
 #pragma unroll
     for (int j = 0; j < nu; j++) out[i * Y::SU + j] = hu[j];
     if (i > 0) {
@@ -370,7 +380,7 @@ __device__ __forceinline__ void lane_sweep_costates(const double* __restrict__ i
   M::dPhidx(lmd, xc, p);
 #pragma unroll
   for (int j = 0; j < nx; j++) lt[(dv - 1) * Y::SXT + j] = lmd[j];
-CG_UNROLL(CG_SWEEP_UNROLL)
+CG_UNROLL((SweepUnroll<M>::value))
   for (int i = dv - 1; i > 0; i--) {
     double xi[nx], hx[nx];
 #pragma unroll

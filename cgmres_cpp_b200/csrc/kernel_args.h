@@ -72,8 +72,16 @@ cudaError_t pipelined_exact_launch_control(int model, bool ptau_full, const Fast
 // third generation (pipe2_update.cuh): FMA build (pipe2_fast_kernels.cu) and bit-exact build (pipe2_exact_kernels.cu)
 cudaError_t pipe2_fast_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
 cudaError_t pipe2_exact_launch_control(int model, bool ptau_full, const FastArgs& a, cudaStream_t s);
-size_t pipe2_scratch_doubles(int model, int device, int64_t n);
-int pipe2_instances_per_cta(int model);
+size_t pipe2_fast_scratch_doubles(int model, int device, int64_t n);
+size_t pipe2_exact_scratch_doubles(int model, int device, int64_t n);
+int pipe2_fast_instances_per_cta(int model);   // (the two builds may hold different numbers of groups per SM)
+int pipe2_exact_instances_per_cta(int model);
+inline size_t pipe2_scratch_doubles(int model, int device, int64_t n, bool exact) {
+  return exact ? pipe2_exact_scratch_doubles(model, device, n) : pipe2_fast_scratch_doubles(model, device, n);
+}
+inline int pipe2_instances_per_cta(int model, bool exact) {
+  return exact ? pipe2_exact_instances_per_cta(model) : pipe2_fast_instances_per_cta(model);
+}
 int fast_instances_per_cta(int model);
 int onchip_exact_instances_per_cta(int model);
 inline int onchip_instances_per_cta(int model, int mode) {  // mode 1 = fast, 2 = onchip_exact, 3 = pipelined exact

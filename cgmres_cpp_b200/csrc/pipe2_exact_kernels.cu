@@ -20,4 +20,22 @@ cudaError_t pipe2_exact_launch_control(int model, bool ptau_full, const FastArgs
   return cudaErrorInvalidValue;
 }
 
+size_t pipe2_exact_scratch_doubles(int model, int device, int64_t n) {
+  switch (model) {
+    case MODEL_MSD: return pipe2::scratch_for<MassSpringDamperModel, true>(device, n);
+    case MODEL_ARM: return pipe2::scratch_for<ArmPendulumModel, true>(device, n);
+    case MODEL_SEMIACTIVE: return pipe2::scratch_for<SemiactiveDamperModel, true>(device, n);
+  }
+  return 0;
+}
+
+int pipe2_exact_instances_per_cta(int model) {
+  switch (model) {
+    case MODEL_MSD: return pipe2::Lay<MassSpringDamperModel, true>::NI;
+    case MODEL_ARM: return pipe2::Lay<ArmPendulumModel, true>::NI;
+    case MODEL_SEMIACTIVE: return pipe2::Lay<SemiactiveDamperModel, true>::NI;
+  }
+  return 1;
+}
+
 }  // namespace cgmres_b200

@@ -20,20 +20,20 @@ cudaError_t pipe2_fast_launch_control(int model, bool ptau_full, const FastArgs&
   return cudaErrorInvalidValue;
 }
 
-size_t pipe2_scratch_doubles(int model, int device, int64_t n) {
+size_t pipe2_fast_scratch_doubles(int model, int device, int64_t n) {
   switch (model) {
-    case MODEL_MSD: return pipe2::scratch_for<MassSpringDamperModel>(device, n);
-    case MODEL_ARM: return pipe2::scratch_for<ArmPendulumModel>(device, n);
-    case MODEL_SEMIACTIVE: return pipe2::scratch_for<SemiactiveDamperModel>(device, n);
+    case MODEL_MSD: return pipe2::scratch_for<MassSpringDamperModel, false>(device, n);
+    case MODEL_ARM: return pipe2::scratch_for<ArmPendulumModel, false>(device, n);
+    case MODEL_SEMIACTIVE: return pipe2::scratch_for<SemiactiveDamperModel, false>(device, n);
   }
   return 0;
 }
 
-int pipe2_instances_per_cta(int model) {
+int pipe2_fast_instances_per_cta(int model) {
   switch (model) {
-    case MODEL_MSD: return pipe2::Lay<MassSpringDamperModel>::NI;
-    case MODEL_ARM: return pipe2::Lay<ArmPendulumModel>::NI;
-    case MODEL_SEMIACTIVE: return pipe2::Lay<SemiactiveDamperModel>::NI;
+    case MODEL_MSD: return pipe2::Lay<MassSpringDamperModel, false>::NI;
+    case MODEL_ARM: return pipe2::Lay<ArmPendulumModel, false>::NI;
+    case MODEL_SEMIACTIVE: return pipe2::Lay<SemiactiveDamperModel, false>::NI;
   }
   return 1;
 }

@@ -10,7 +10,7 @@ namespace pipe2 {
 
 template <class M, class Sim, bool EXACT>
 cudaError_t launch(bool pfull, const FastArgs& a, cudaStream_t s) {
-  using Y = Lay<M>;
+  using Y = Lay<M, EXACT>;
   if (a.n == 0) return cudaSuccess;
   if (a.scratch == nullptr) return cudaErrorInvalidValue;
   if (a.n_steps > 1 && a.dtau_tab == nullptr && a.t_inst == nullptr) return cudaErrorInvalidValue;
@@ -34,9 +34,9 @@ cudaError_t launch(bool pfull, const FastArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-template <class M>
+template <class M, bool EXACT>
 size_t scratch_for(int device, int64_t n) {
-  using Y = Lay<M>;
+  using Y = Lay<M, EXACT>;
   const int64_t rounds = (n + Y::NI - 1) / Y::NI;
   const int64_t ctas = rounds < (int64_t)pipe::sm_count(device) ? rounds : (int64_t)pipe::sm_count(device);
   return (size_t)(ctas > 0 ? ctas : 1) * Y::scratch_doubles_per_cta;

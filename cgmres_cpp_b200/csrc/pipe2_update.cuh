@@ -40,23 +40,43 @@ using pipe::l2_evict_last_policy;
 using pipe::ld_keep;
 using pipe::st_keep;
 
+// groups in flight per SM, at most.  Measured (msd 65,536 / semiactive 131,072 instances, updates/s): a third msd group
+// (compact plane layout below) is SLOWER, 5.4e7 vs 6.6e7; semiactive gains from a third group, bit-exact build 7.1e7 ->
+// 8.1e7, FMA build 1.30e8 -> 1.35e8; arm loses (1.3e7 -> 1.1e7).  So: three groups for models with short vector slices
+// and a two-state sweep, two otherwise.
 #ifndef CG_PIPE2_NGMAX
-#define CG_PIPE2_NGMAX 2
+#define CG_PIPE2_NGMAX(Q, NX) (((Q) <= 5 && (NX) <= 2) ? 3 : 2)
 #endif
 
-template <class M>
+#ifndef CG_PIPE2_COMPACT
+#define CG_PIPE2_COMPACT 0  // measured: a third msd group is SLOWER (5.4e7 vs 6.6e7 updates/s), see profiles/README.md
+#endif
+
+template <class M, bool EXACT>
 struct Lay {
   using F = fast::Lay<M>;
   static constexpr int nx = F::nx, nu = F::nu, np = F::np, dv = F::dv, km = F::km, L = F::L, np1 = F::np1;
-  static constexpr int SXT = F::SXT, XT = F::XT, LTN = F::LTN, Q = F::Q;
+  static constexpr int Q = F::Q;
+  // COMPACT plane: models whose dHdu ignores x (Model::dHdu_reads_x == false) keep ONE plane of dv+1 unpadded rows per
+  // instance: the rollout writes x_i into row i, the costate recursion overwrites row i with lambda_i once x_i has
+  // been consumed, the stage-parallel dHdu reads lambda_{i+1} from row i+1.  That is 204 instead of 495 doubles for
+  // mass_spring_damper and lets a third group of instances fit in shared memory.  (The bit-exact build parks a basis
+  // vector of L doubles in the planes during Gram-Schmidt and therefore keeps the two-plane layout.)
+  static constexpr bool compact = CG_PIPE2_COMPACT && !M::dHdu_reads_x && !EXACT;
+  static constexpr int SXT = compact ? nx : F::SXT;
+  static constexpr int XT = compact ? (dv + 1) * nx : F::XT;
+  static constexpr int LTN = compact ? 0 : F::LTN;
   static_assert(F::SU == nu, "unpadded dim_u rows");
-  static constexpr int GI = 16;  // instances per group = vector warps per CTA
+#ifndef CG_PIPE2_GI
+#define CG_PIPE2_GI 16
+#endif
+  static constexpr int GI = CG_PIPE2_GI;  // instances per group = vector warps per CTA
   // per-instance shared-memory block (doubles)
   static constexpr int oX = 0;          // sweep input U (+ h*v) -> F in place; EXACT: element products of a sum
   static constexpr int oXT = oX + L;    // rollout states xtau[1..dv-1] (padded rows)
   static constexpr int oLT = oXT + XT;  // costates ltau[1..dv]
   static constexpr int oS = oLT + LTN;  // scalars
-  static_assert(XT + LTN >= L, "the Gram-Schmidt basis vector is parked in the rollout/costate planes");
+  static_assert(!EXACT || XT + LTN >= L, "the Gram-Schmidt basis vector is parked in the rollout/costate planes");
   static constexpr int sR = 0;                        // packed upper triangle R(i,j), i<=j<km
   static constexpr int sG = sR + km * (km + 1) / 2;   // 3*km reflectors
   static constexpr int sX = sG + 3 * km;              // x
@@ -73,17 +93,26 @@ struct Lay {
   static constexpr int raw = oS + sCount;
   static constexpr int stride = (raw % 2 == 0) ? raw + 1 : raw;  // odd: lane-per-instance accesses hit distinct banks
   static constexpr int NG_fit = (fast::kSmemBudget - 64) / (GI * stride * 8);
-  static constexpr int NG = NG_fit < 2 ? 2 : (NG_fit > CG_PIPE2_NGMAX ? CG_PIPE2_NGMAX : NG_fit);
+  static constexpr int NG = NG_fit < 2 ? 2 : (NG_fit > CG_PIPE2_NGMAX(Q, nx) ? CG_PIPE2_NGMAX(Q, nx) : NG_fit);
   static constexpr int NI = GI * NG;
   static constexpr int NVEC = km + 1;  // stored vectors per instance: id 0 = F1, id 1+i = v_i (v_0's slot first holds b)
   static constexpr int tcols_vec = 2 * Q;
-  // warp roles: serial warps 0, 4, ..; vector warp v < 15 is warp 1 + v + v/3, the 16th is warp 4*NG
+  // warp roles.  CG_PIPE2_SPREAD = 1: warps 0..NG-1 are the serial warps (warp g on scheduler / TMEM lane quarter g),
+  // warps NG..NG+GI-1 the vector warps, spread evenly over the four schedulers: the serial warps do NOT share an FP64
+  // pipe with each other (a sweep alone keeps ~50 % of one sub-partition's FP64 issue slots busy; two serial warps on
+  // one scheduler slowed each other 1.5x, tools/micro/fp64_interference.cu).  CG_PIPE2_SPREAD = 0: the second
+  // generation's placement (serial warps 0, 4, .. all on scheduler 0; vector warps on schedulers 1..3, the 16th on 0).
+#ifndef CG_PIPE2_SPREAD
+#define CG_PIPE2_SPREAD 1
+#endif
+  static constexpr bool spread = CG_PIPE2_SPREAD != 0;
   static constexpr int GV3 = GI < 15 ? GI : 15;
-  static constexpr int last_vec_wid = 1 + (GV3 - 1) + (GV3 - 1) / 3;
-  static constexpr int last_s0_wid = 4 * (NG - 1 + GI - GV3);
+  static constexpr int last_vec_wid = spread ? NG + GI - 1 : 1 + (GV3 - 1) + (GV3 - 1) / 3;
+  static constexpr int last_s0_wid = spread ? NG - 1 : 4 * (NG - 1 + GI - GV3);
   static constexpr int NW = (last_vec_wid > last_s0_wid ? last_vec_wid : last_s0_wid) + 1;
-  static constexpr int wq = (last_vec_wid >> 2) + 1;  // column groups of the TMEM allocation (warp id / 4)
-  static_assert(last_s0_wid <= last_vec_wid, "warps 4, 8, .. reuse existing column groups");
+  // column groups of the TMEM allocation: vector warps that share a lane quarter (warp id % 4) need distinct columns
+  static constexpr int wq = spread ? (GI + 3) / 4 : (last_vec_wid >> 2) + 1;
+  static_assert(spread || last_s0_wid <= last_vec_wid, "warps 4, 8, .. reuse existing column groups");
   static constexpr int NVT_fit = 512 / (wq * NG * tcols_vec);
   static constexpr int NVT = NVT_fit < NVEC ? NVT_fit : NVEC;  // vectors of an instance kept in TMEM
   static_assert(NVT >= 2, "F1 and b / v_0 must fit in tensor memory");
@@ -109,35 +138,81 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // sum_{j=0..L-1} p[j] in index order starting from 0 (matrix.hpp:140-159), one lane per instance: the loads of the
 // next batch are in flight while the current batch is added (the adds are one dependent chain by definition)
+#ifndef CG_SUM_DEPTH
+#define CG_SUM_DEPTH 3  // batches of 10 shared-memory loads in flight ahead of the dependent adds
+#endif
 template <int L>
 __device__ __forceinline__ double lane_seq_sum(const double* __restrict__ p) {
-  constexpr int BS = 10;
-  double acc = 0.0;
-  double cur[BS], nxt[BS];
+  constexpr int BS = 10, D = CG_SUM_DEPTH;
   constexpr int NB = L / BS;
-  if (NB > 0) {
+  double acc = 0.0;
+  double buf[D][BS];
 #pragma unroll
-    for (int q = 0; q < BS; q++) cur[q] = p[q];
-  }
-#pragma unroll 2
-  for (int b = 0; b < NB; b++) {
-    if (b + 1 < NB) {
+  for (int d = 0; d < D; d++) {
+    if (d < NB) {
 #pragma unroll
-      for (int q = 0; q < BS; q++) nxt[q] = p[(b + 1) * BS + q];
+      for (int q = 0; q < BS; q++) buf[d][q] = p[d * BS + q];
     }
+  }
 #pragma unroll
-    for (int q = 0; q < BS; q++) acc += cur[q];
+  for (int b = 0; b < NB; b++) {  // fully unrolled: every buffer index is static, no register moves
 #pragma unroll
-    for (int q = 0; q < BS; q++) cur[q] = nxt[q];
+    for (int q = 0; q < BS; q++) acc += buf[b % D][q];
+    if (b + D < NB) {
+#pragma unroll
+      for (int q = 0; q < BS; q++) buf[b % D][q] = p[(b + D) * BS + q];
+    }
   }
 #pragma unroll
   for (int j = NB * BS; j < L; j++) acc += p[j];
   return acc;
 }
 
+// COMPACT-plane sweep (see Lay::compact): rollout + costate recursion of one instance by one lane, one plane P of
+// dv+1 rows of dim_x doubles.  On return row i+1 holds lambda_{i+1} = ltau[i+1] for i = 0..dv-1 (cgmres.hpp:132-153).
+template <class M, bool PFULL>
+__device__ __forceinline__ void lane_sweep_compact(const double* __restrict__ in, double* __restrict__ P,
+                                                   const double* __restrict__ x0, const double dtau,
+                                                   const double* __restrict__ pconst,
+                                                   const double* __restrict__ pfull) {
+  constexpr int nx = M::dim_x, nu = M::dim_u, np = M::dim_p, dv = M::dv;
+  constexpr int np1 = np > 0 ? np : 1;
+  double xc[nx], lmd[nx], u[nu], p[np1];
+#pragma unroll
+  for (int j = 0; j < np; j++) p[j] = pconst[j];
+  // rows 1..dv-1 <- xtau[1..dv-1]; xtau[dv] stays in xc
+  fast::lane_rollout<M, PFULL, nx>(in, P + nx, x0, dtau, pconst, pfull, xc);
+  if (PFULL) {
+#pragma unroll
+    for (int j = 0; j < np; j++) p[j] = pfull[dv * np + j];
+  }
+  M::dPhidx(lmd, xc, p);  // cgmres.hpp:145
+#pragma unroll
+  for (int j = 0; j < nx; j++) P[dv * nx + j] = lmd[j];
+CG_UNROLL((fast::SweepUnroll<M>::value))
+  for (int i = dv - 1; i > 0; i--) {
+    double xi[nx], hx[nx];
+#pragma unroll
+    for (int j = 0; j < nx; j++) xi[j] = P[i * nx + j];
+#pragma unroll
+    for (int j = 0; j < nu; j++) u[j] = in[i * nu + j];
+    if (PFULL) {
+#pragma unroll
+      for (int j = 0; j < np; j++) p[j] = pfull[i * np + j];
+    }
+    M::dHdx(hx, xi, u, p, lmd);
+#pragma unroll
+    for (int j = 0; j < nx; j++) {
+      double m = hx[j] * dtau;
+      lmd[j] = m + lmd[j];
+      P[i * nx + j] = lmd[j];  // lambda_i over x_i
+    }
+  }
+}
+
 template <class M, class Sim, bool PFULL, bool EXACT>
-__global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastArgs a) {
-  using Y = Lay<M>;
+__global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(const FastArgs a) {
+  using Y = Lay<M, EXACT>;
   constexpr int nx = Y::nx, nu = Y::nu, np = Y::np, L = Y::L, km = Y::km, Q = Y::Q, GI = Y::GI, NG = Y::NG, NI = Y::NI;
   constexpr int T = Y::bar_threads;
   constexpr double hh = M::h;
@@ -145,8 +220,9 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   constexpr double c1 = (1 - M::zeta * M::h);
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int sg = ((wid & 3) == 0 && (wid >> 2) < NG) ? (wid >> 2) : -1;
-  const int vw_ = (wid & 3) ? wid - 1 - (wid >> 2) : ((wid >> 2) >= NG ? Y::GV3 + (wid >> 2) - NG : -1);
+  const int sg = Y::spread ? (wid < NG ? wid : -1) : (((wid & 3) == 0 && (wid >> 2) < NG) ? (wid >> 2) : -1);
+  const int vw_ = Y::spread ? wid - NG
+                            : ((wid & 3) ? wid - 1 - (wid >> 2) : ((wid >> 2) >= NG ? Y::GV3 + (wid >> 2) - NG : -1));
   const int vw = (vw_ >= 0 && vw_ < GI) ? vw_ : -1;
   const int64_t nrounds = (a.n + NI - 1) / NI;
   const int64_t prow = (int64_t)(PFULL ? (M::dv + 1) * np : np);
@@ -167,7 +243,6 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
 
   auto BX = [](int g) { return 1 + g; };
   auto BL = [](int g) { return 1 + NG + g; };
-  double* const scr_cta = a.scratch + (size_t)blockIdx.x * Y::scratch_doubles_per_cta;
 #ifdef CG_PIPE_TIMING
   long long t_wait = 0, t_sw = 0, t_sum = 0, t_dh = 0, t_fin = 0, t_si = 0, t_lap = 0;
   (void)t_lap;
@@ -188,8 +263,12 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         { CG_PIPE_WAIT_BEGIN; bar_sync(BX(g), T); CG_PIPE_WAIT_END(t_wait); }
         if (lane < n_here && (!check_flag || s[Y::sFLAG] == 0.0)) {
           CG_PIPE_WORK_BEGIN;
-          fast::lane_sweep_costates<M, PFULL>(b + Y::oX, b + Y::oXT, b + Y::oLT, at_x ? s + Y::sX : s + Y::sXH,
-                                              at_x ? s[Y::sDT] : s[Y::sDT + 1], s + Y::sP, pf);
+          if (Y::compact)
+            lane_sweep_compact<M, PFULL>(b + Y::oX, b + Y::oXT, at_x ? s + Y::sX : s + Y::sXH,
+                                         at_x ? s[Y::sDT] : s[Y::sDT + 1], s + Y::sP, pf);
+          else
+            fast::lane_sweep_costates<M, PFULL>(b + Y::oX, b + Y::oXT, b + Y::oLT, at_x ? s + Y::sX : s + Y::sXH,
+                                                at_x ? s[Y::sDT] : s[Y::sDT + 1], s + Y::sP, pf);
           CG_PIPE_WORK_END(t_sw);
         }
         bar_arrive(BL(g), T);
@@ -218,12 +297,17 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
   } else if (vw >= 0) {
     // =============================== vector warps: warp = instance (of each group) ================================
     const uint64_t keep = l2_evict_last_policy();
-    const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (wid & 3)) << 16) + (uint32_t)((wid >> 2) * Y::tcols_warp);
+    const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (wid & 3)) << 16) +
+                           (uint32_t)((Y::spread ? (vw >> 2) : (wid >> 2)) * Y::tcols_warp);
     double W[EXACT ? NG : 1][Q];  // EXACT: working vector slice of each group across the sum hand-offs
 
     auto blk_of = [&](int g) { return sm + (size_t)(g * GI + vw) * Y::stride; };
     auto tslot_of = [&](int g) { return tbase + (uint32_t)(g * Y::tcols_slot); };
-    auto scr_of = [&](int g) { return scr_cta + (size_t)(g * GI + vw) * (Y::NSCR > 0 ? Y::NSCR : 1) * L; };
+    // (recomputed from the kernel parameter on every use: a live 64-bit register less through the whole kernel)
+    auto scr_of = [&](int g) {
+      return a.scratch + (size_t)blockIdx.x * Y::scratch_doubles_per_cta +
+             (size_t)(g * GI + vw) * (Y::NSCR > 0 ? Y::NSCR : 1) * L;
+    };
 
     auto vec_store = [&](int id, int g, const double* v) {
       if (id < Y::NVT) {
@@ -289,8 +373,13 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         double xi[nx], u[nu], p[Y::np1], lm[nx], hu[nu];
 #pragma unroll
         for (int j = 0; j < nx; j++) {
-          xi[j] = (i > 0) ? blk[Y::oXT + (i - 1) * Y::SXT + j] : x0[j];
-          lm[j] = blk[Y::oLT + i * Y::SXT + j];
+          if (Y::compact) {  // dHdu ignores x; lambda_{i+1} sits in row i+1 of the single plane
+            xi[j] = 0.0;
+            lm[j] = blk[Y::oXT + (i + 1) * nx + j];
+          } else {
+            xi[j] = (i > 0) ? blk[Y::oXT + (i - 1) * Y::SXT + j] : x0[j];
+            lm[j] = blk[Y::oLT + i * Y::SXT + j];
+          }
         }
 #pragma unroll
         for (int j = 0; j < nu; j++) u[j] = blk[Y::oX + i * nu + j];

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
         const int64_t n0 = r * NI + (int64_t)g * GI;
         const int n_here = (int)((a.n - n0) < (int64_t)GI ? ((a.n - n0) > 0 ? (a.n - n0) : 0) : (int64_t)GI);
         { CG_PIPE_WAIT_BEGIN; bar_sync(BX(g), T); CG_PIPE_WAIT_END(t_wait); }
+        const unsigned pair_mask = __ballot_sync(0xffffffffu, lane < 2 * n_here);  // the lanes that run pass 1
         if (lane < 2 * n_here) {
           const int inst = lane >> 1, tr = lane & 1;
           double* b = sm + (size_t)(g * GI + inst) * Y::stride;
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(Lay<M>::threads, 1) control_kernel(const FastA
           const double dtau = tr == 0 ? s[Y::sDT + 1] : s[Y::sDT];
           double* plane = b + (tr == 0 ? Y::oXT : Y::oLT);
           CG_PIPE_WORK_BEGIN;
-          fast::lane_sweep_full<M, PFULL, Y::SXT>(b + Y::oX, out, plane, x0p, dtau, s + Y::sP, pf);
+          // (the even lane overwrites X in place while the odd lane of the pair still reads it: share_mask)
+          fast::lane_sweep_full<M, PFULL, Y::SXT>(b + Y::oX, out, plane, x0p, dtau, s + Y::sP, pf, pair_mask);
           CG_PIPE_WORK_END(t_p1);
         }
         bar_arrive(BL(g), T);

@@ -122,8 +122,10 @@ int cgmres_b200_get_u(cgmres_b200_handle h, double* u);
  * <example>/main.cpp:66-77 (forward Euler).  Asynchronous on the handle's stream. */
 int cgmres_b200_step_closed_loop(cgmres_b200_handle h, int n_steps);
 /* (MODE_FAST / MODE_PIPELINED_EXACT run n_steps > 1 as multi-step launches of the persistent kernel: the same resident
- *  instances advance up to 256 steps per launch, per-step horizon ramps from a host-evaluated table.  Results are the
- *  ones of n_steps single-step calls, bit for bit.) */
+ *  instances advance up to 256 steps per launch, per-step horizon ramps from a host-evaluated table.  In the bit-exact
+ *  mode the results are those of n_steps single-step calls bit for bit; in MODE_FAST likewise for batches larger than
+ *  16 instances per SM -- smaller batches take a shorter-latency kernel for single-step calls, whose FMA contraction
+ *  may differ in the last bit.) */
 
 /* The same loop with the trajectory recorded ON THE DEVICE and copied out chunk-wise: x_log[n_steps][n][dim_x] = the
  * plant state after every step, u_log[n_steps][n][dim_u] = the input every control update returned -- the rows the

@@ -68,6 +68,9 @@ struct MassSpringDamperModel : SolverDefaults, MassSpringDamperPlantConstants {
   static constexpr uint16_t dim_p = 2;
   static constexpr uint16_t dv = 50;
   static constexpr double Tf = 1.0;
+  // kernel hint (not part of the reference's contract): dHdu below ignores its x argument (the plant is linear in u
+  // with constant gains), so the on-chip kernels may let the costates overwrite the rollout states in place
+  static constexpr bool dHdu_reads_x = false;
 
   // weights, model.hpp:112-115
   static constexpr double sf0 = 10.0, sf1 = 10.0, sf2 = 1.0, sf3 = 1.0;
@@ -158,6 +161,7 @@ struct ArmPendulumModel : SolverDefaults, ArmPendulumPlantConstants {
   static constexpr uint16_t dim_p = 2;
   static constexpr uint16_t dv = 25;
   static constexpr double Tf = 0.5;
+  static constexpr bool dHdu_reads_x = true;  // cos(x0 - x1) in dHdu
 
   static constexpr double sf0 = 3.0, sf1 = 1.0, sf2 = 0.0, sf3 = 0.0;  // model.hpp:81
   static constexpr double q0 = 1.0, q1 = 1.0, q2 = 0.0, q3 = 0.0;      // model.hpp:82
@@ -235,6 +239,7 @@ struct SemiactiveDamperModel : SolverDefaults, SemiactiveDamperPlantConstants {
   static constexpr uint16_t dim_p = 0;
   static constexpr uint16_t dv = 50;
   static constexpr double Tf = 1.0;
+  static constexpr bool dHdu_reads_x = true;  // b*x[1]*lmd[1] in dHdu
 
   static constexpr double sf0 = 1.0, sf1 = 10.0;  // model.hpp:74
   static constexpr double q0 = 1.0, q1 = 10.0;    // model.hpp:75

@@ -7,6 +7,7 @@ cd "$(dirname "$0")/../cgmres_cpp_b200/csrc"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="$ARCH -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -I../../include -I. -DCG_ONLY_MSD $*"
 mkdir -p ../_build_quick
+make -s ../_build/capi.o ../_build/layout.o ../_build/peak.o > /dev/null  # host side: always current
 nvcc $COMMON -Xptxas -v -c pipe2_fast_kernels.cu -o ../_build_quick/pipe2_fast_kernels.o 2> ../_build_quick/pipe2_fast.log &
 nvcc $COMMON -fmad=false -Xptxas -v -c pipe2_exact_kernels.cu -o ../_build_quick/pipe2_exact_kernels.o 2> ../_build_quick/pipe2_exact.log
 wait
