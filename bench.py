@@ -33,7 +33,11 @@ sys.path.insert(0, ROOT)
 # its share of the box's cores instead of torchrun's blanket OMP_NUM_THREADS=1.  Must happen before libgomp loads.
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     _lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, _lws)))
+    # one core of the share stays with the rank's main thread (it spins in the CUDA synchronisation), and idle OpenMP
+    # workers must SLEEP between plant steps: with the default active wait policy 8 ranks x (workers + main) spin on
+    # more threads than the box has cores and every rank's loop slows down (round 1: e2e scaling 0.915 at 8 GPUs)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, _lws) - 1))
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 METRIC = "batched C/GMRES control updates/sec"
 UNIT = "updates/s"
@@ -123,7 +127,7 @@ def visible_gpu_index(local_rank: int) -> int:
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_baseline_run(model_id: int, n_inst: int, steps: int, threads: int, seed: int = 12345):
+def cpu_baseline_run(model_id: int, n_inst: int, steps: int, threads: int, seed: int = 12345, n_total: int = 0):
     """The reference's CPU path on `threads` host threads over the first n_inst instances of the GPU workload.
 
     Throughput uses the wall time of the closed-loop step loops alone (max over the worker threads, measured inside
@@ -132,7 +136,10 @@ def cpu_baseline_run(model_id: int, n_inst: int, steps: int, threads: int, seed:
     from oracle import pyoracle as po
 
     ora = po.best()
-    x0, p, u0 = po.synthetic_batch(model_id, n_inst, seed=seed)
+    # the FIRST n_inst instances of the n_total-instance batch the GPU arm runs (the generator draws whole columns, so
+    # a batch generated at another size is a different batch)
+    x0, p, u0 = po.synthetic_batch(model_id, max(n_total, n_inst), seed=seed)
+    x0, p = x0[:n_inst], p[:n_inst]
     t0 = time.perf_counter()
     out = ora.run_closed_loop(model_id, x0, p, u0, steps, n_threads=threads)
     wall = time.perf_counter() - t0
@@ -152,8 +159,8 @@ def run_reference_arm(args, rank: int):
     # bounded sample: a few instances per core, every step advances all of them by one closed-loop step
     n_inst = min(n_per_gpu, cores * max(1, args.cpu_instances_per_core))
     if args.warmup > 0:
-        cpu_baseline_run(model_id, n_inst, args.warmup, cores)
-    r = cpu_baseline_run(model_id, n_inst, args.steps, cores)
+        cpu_baseline_run(model_id, n_inst, args.warmup, cores, n_total=n_per_gpu)
+    r = cpu_baseline_run(model_id, n_inst, args.steps, cores, n_total=n_per_gpu)
     value = r["updates"] / r["loop_s"]
     sample = (f"first {n_inst} instances of the seeded {n_per_gpu}-instance batch x {args.steps} closed-loop steps, "
               f"{cores} host threads, one live controller per thread; timed: the step loops only (set-up excluded)")
@@ -462,7 +469,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = prof.get(f"{model}_{headline}_{n}", {}).get("dram_bytes_per_launch")
+            ent = prof.get(f"{model}_{headline}_{n}", {})
+            # (per closed-loop step, like `achieved`: the third-generation kernel advances several steps per launch)
+            traffic = ent.get("dram_bytes_per_step", ent.get("dram_bytes_per_launch"))
         except Exception:
             pass
         for c in configs.values():
@@ -526,7 +535,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             cores = os.cpu_count() or 1
             n_cpu = min(n, cores * max(1, args.cpu_instances_per_core))
             cpu_steps = warmup + steps  # the GPU run's closed-loop length (warm-up included): end states comparable
-            r = cpu_baseline_run(model_id, n_cpu, cpu_steps, cores)
+            r = cpu_baseline_run(model_id, n_cpu, cpu_steps, cores, n_total=n)
             v = r["updates"] / r["loop_s"]
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": r["kind"], "per_core": v / cores,

@@ -307,6 +307,32 @@ def test_cpp_dropin_example_reproduces_reference_text_output(cg, oracle_best, tm
             assert lines[i] == ref_line, (name, i)
 
 
+@pytest.mark.parametrize("how", ["host", "device"])
+def test_cpp_example_multiple_controller_runs_both_controllers_in_one_loop(cg, oracle_best, tmp_path, how):
+    """examples/closed_loop multiple_controller: a Model1 and a Model2 controller stepped alternately inside one loop
+    (multiple_controller/main.cpp:104-118; device mode: two handles, trajectory logged in device memory).  Both logs
+    equal the single-controller runs (the controllers never interact), line for line."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "closed_loop")
+    steps = 300
+    r = subprocess.run([exe, "multiple_controller", "2", how, str(steps)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    s = po.SHIPPED[po.MSD]
+    want = oracle_best.run_closed_loop(po.MSD, [s["x0"]], [s["p"]], s["u0"], steps, rec_stride=1)
+    lines = (tmp_path / "multiple_controller_1_x.txt").read_text().splitlines()
+    assert len(lines) == steps
+    for i in (0, 150, steps - 1):
+        assert lines[i] == "%f" % (0.001 * i) + "".join("\t%f" % v for v in want["x_traj"][i, 0]), i
+    s = po.SHIPPED[po.ARM]
+    want = po.load("port_ptrig").run_closed_loop(po.ARM, [s["x0"]], [s["p"]], s["u0"], steps, rec_stride=1)
+    lines = (tmp_path / "multiple_controller_2_u.txt").read_text().splitlines()
+    assert len(lines) == steps
+    for i in (0, 150, steps - 1):
+        assert lines[i] == "%f" % (0.001 * i) + "".join("\t%f" % v for v in want["u_traj"][i, 0]), i
+
+
 def test_multiple_controller_heterogeneous_batch(cg, oracle_best):
     """BASELINE config 5 / multiple_controller/main.cpp:89-118: a Model1 (mass_spring_damper) batch and a Model2
     (arm_type_inverted_pendulum) batch advance side by side on one GPU, each handle on its own stream, interleaved
