@@ -33,11 +33,10 @@ sys.path.insert(0, ROOT)
 # its share of the box's cores instead of torchrun's blanket OMP_NUM_THREADS=1.  Must happen before libgomp loads.
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     _lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-    # one core of the share stays with the rank's main thread (it spins in the CUDA synchronisation), and idle OpenMP
-    # workers must SLEEP between plant steps: with the default active wait policy 8 ranks x (workers + main) spin on
-    # more threads than the box has cores and every rank's loop slows down (round 1: e2e scaling 0.915 at 8 GPUs)
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, _lws) - 1))
-    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    # measured on the 8-GPU box (tools/e2e_scaling.py, profiles/r02_e2e_scaling_8gpu.txt): 4 threads with the default
+    # (active) wait policy 1.30-1.38 ms per e2e step, 2 threads 1.36, 1 thread 1.50, 3 threads with
+    # OMP_WAIT_POLICY=passive 1.77 (sleeping workers wake up too slowly for a 0.1 ms plant step); 1 GPU alone: 1.24
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, _lws)))
 
 METRIC = "batched C/GMRES control updates/sec"
 UNIT = "updates/s"

@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
     auto stage_dhdu = [&](double* blk, const double* sc, const double* x0, int64_t n) {
       CG_PIPE_WORK_BEGIN;
       const double* pf = PFULL ? a.ptau + n * prow : nullptr;
+      const bool x16 = ((uint32_t)__cvta_generic_to_shared(blk + Y::oX) & 15u) == 0;  // warp-uniform
       for (int i = lane; i < M::dv; i += 32) {
         double xi[nx], u[nu], p[Y::np1], lm[nx], hu[nu];
 #pragma unroll
@@ -381,13 +382,46 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
             lm[j] = blk[Y::oLT + i * Y::SXT + j];
           }
         }
+        // u_i / F_i rows: with an even dim_u the row stride (dim_u doubles) puts lanes i and i + 8 on the same banks, a
+        // 4-way conflict for 8-byte accesses but none for 16-byte ones (8 consecutive rows cover 8 distinct 16-byte
+        // segments of a 128-byte line).  The block stride is odd, so an instance block is 16-byte aligned or 8 bytes off
+        // (warp-uniform): pairs (0,1),(2,3).. or a scalar head, pairs (1,2),(3,4).., a scalar tail.
+        double* row = blk + Y::oX + i * nu;
+        if (nu % 2 == 0 && x16) {
 #pragma unroll
-        for (int j = 0; j < nu; j++) u[j] = blk[Y::oX + i * nu + j];
+          for (int j = 0; j < nu; j += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(row + j);
+            u[j] = t.x;
+            u[j + 1] = t.y;
+          }
+        } else if (nu % 2 == 0) {
+          u[0] = row[0];
+#pragma unroll
+          for (int j = 1; j + 1 < nu; j += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(row + j);
+            u[j] = t.x;
+            u[j + 1] = t.y;
+          }
+          u[nu - 1] = row[nu - 1];
+        } else {
+#pragma unroll
+          for (int j = 0; j < nu; j++) u[j] = row[j];
+        }
 #pragma unroll
         for (int j = 0; j < np; j++) p[j] = PFULL ? pf[i * np + j] : sc[Y::sP + j];
         M::dHdu(hu, xi, u, p, lm);
+        if (nu % 2 == 0 && x16) {
 #pragma unroll
-        for (int j = 0; j < nu; j++) blk[Y::oX + i * nu + j] = hu[j];
+          for (int j = 0; j < nu; j += 2) *reinterpret_cast<double2*>(row + j) = make_double2(hu[j], hu[j + 1]);
+        } else if (nu % 2 == 0) {
+          row[0] = hu[0];
+#pragma unroll
+          for (int j = 1; j + 1 < nu; j += 2) *reinterpret_cast<double2*>(row + j) = make_double2(hu[j], hu[j + 1]);
+          row[nu - 1] = hu[nu - 1];
+        } else {
+#pragma unroll
+          for (int j = 0; j < nu; j++) row[j] = hu[j];
+        }
       }
       __syncwarp();
       CG_PIPE_WORK_END(t_dh);
