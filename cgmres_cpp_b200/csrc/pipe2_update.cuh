@@ -700,8 +700,8 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
     };
 
     // ---- end of a step of (round r, group g): what the group does next ---------------------------------------------
-    // returns true when a final update of (r, g) is still owed (deferred into the next round's first phase)
-    auto end_of_step = [&](int64_t r, int g, int step, bool more_rounds) -> bool {
+    // (when another round follows, the final update of (r, g) is deferred into that round's first phase)
+    auto end_of_step = [&](int64_t r, int g, int step, bool more_rounds) {
       const int64_t n = r * NI + (int64_t)g * GI + vw;
       double* blk = blk_of(g);
       double* sc = blk + Y::oS;
@@ -711,15 +711,14 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
         { CG_PIPE_WORK_BEGIN; final_update(r, g, step); CG_PIPE_WORK_END(t_fin); }
         { CG_PIPE_WORK_BEGIN; state_in(r, g, step + 1); CG_PIPE_WORK_END(t_si); }
         bar_arrive(BX(g), T);
-        return false;
+        return;
       }
       if (more_rounds) {  // next round's state first, so that the serial warp never waits for a round to drain
         { CG_PIPE_WORK_BEGIN; state_in(r + gridDim.x, g, 0); CG_PIPE_WORK_END(t_si); }
         bar_arrive(BX(g), T);
-        return true;
+        return;
       }
       { CG_PIPE_WORK_BEGIN; final_update(r, g, step); CG_PIPE_WORK_END(t_fin); }
-      return false;
     };
 
     if ((int64_t)blockIdx.x < nrounds) {
@@ -729,7 +728,6 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
         bar_arrive(BX(g), T);
       }
     }
-    bool owed = false;  // final updates of the previous round still pending (all groups)
 
     for (int64_t r = blockIdx.x; r < nrounds; r += gridDim.x) {
       const bool more = r + gridDim.x < nrounds;
@@ -740,7 +738,8 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
           const int64_t n = r * NI + (int64_t)g * GI + vw;
           const bool has = n < a.n;
           double* blk = blk_of(g);
-          if (owed && step == 0) {  // overlaps the serial warp's sweep
+          // the previous round of this CTA deferred its final updates to here, where they overlap the serial warp's sweep
+          if (r != (int64_t)blockIdx.x && step == 0) {
             CG_PIPE_WORK_BEGIN;
             final_update(r - gridDim.x, g, n_steps - 1);
             CG_PIPE_WORK_END(t_fin);
@@ -850,7 +849,6 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
         }
 
         // ---- Arnoldi iterations ---------------------------------------------------------------------------------
-        bool owed_next = false;
         auto iteration = [&](auto kc) {
           constexpr int k = decltype(kc)::value;
           // after the sweep: w = A v_k = (F - F1)/h (cgmres.hpp:173-174, gmres.hpp:48), then Gram-Schmidt
@@ -915,7 +913,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
               if (k + 1 < km)
                 bar_arrive(BX(g), T);
               else
-                owed_next = end_of_step(r, g, step, more) || owed_next;
+                end_of_step(r, g, step, more);
             } else {
               bar_arrive(BX(g), T);
             }
@@ -978,7 +976,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
               if (k + 1 < km)
                 bar_arrive(BX(g), T);
               else
-                owed_next = end_of_step(r, g, step, more) || owed_next;
+                end_of_step(r, g, step, more);
             }
           }
         };
@@ -988,7 +986,6 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
         if (km > 3) iteration(std::integral_constant<int, (km > 3 ? 3 : 0)>{});
         if (km > 4) iteration(std::integral_constant<int, (km > 4 ? 4 : 0)>{});
         static_assert(km <= 5, "unrolled for k_max <= 5 (every shipped model uses 5)");
-        owed = owed_next;
       }
     }
   }
