@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
   auto BL = [](int g) { return 1 + NG + g; };
 #ifdef CG_PIPE_TIMING
   long long t_wait = 0, t_sw = 0, t_sum = 0, t_dh = 0, t_fin = 0, t_si = 0, t_lap = 0;
+  long long t_p1 = 0, t_p2 = 0, t_p3 = 0, t_it = 0, t_mg = 0, t_fi = 0;
   (void)t_lap;
   const long long t_begin = clock64();
 #endif
@@ -746,6 +747,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
           }
           { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
           if (has) {
+            CG_PIPE_WORK_BEGIN;
             const double* __restrict__ Ug = a.U + n * (int64_t)L;
             double uu[Q], f1[Q];
 #pragma unroll
@@ -758,6 +760,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
             vec_store(0, g, f1);
             sm_put(blk + Y::oX, uu);
             __syncwarp();
+            CG_PIPE_WORK_END(t_p1);
           }
           bar_arrive(BX(g), T);
         }
@@ -769,6 +772,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
           double* blk = blk_of(g);
           { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
           if (has) {
+            CG_PIPE_WORK_BEGIN;
             stage_dhdu(blk, blk + Y::oS, blk + Y::oS + Y::sX, n);
             double dd[Q];  // dUdt: an L2 hit (state_in prefetched the lines), in flight during the TMEM round trip
             {
@@ -791,6 +795,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
             vec_store(1, g, bb);
             form_x(blk, a.U + n * (int64_t)L, dd);
             __syncwarp();
+            CG_PIPE_WORK_END(t_p2);
           }
           bar_arrive(BX(g), T);
         }
@@ -805,6 +810,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
 #pragma unroll
           for (int q = 0; q < Q; q++) w[q] = 0.0;
           if (has) {
+            CG_PIPE_WORK_BEGIN;
             stage_dhdu(blk, blk + Y::oS, blk + Y::oS + Y::sXH, n);
             double fa[Q], bb[Q], fc[Q];
             vec_load(0, g, fa);
@@ -829,6 +835,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
               for (int q = 0; q < Q; q++) ssq += w[q] * w[q];
               after_norm0(blk, g, n, fast::warp_sum(ssq), w);
             }
+            CG_PIPE_WORK_END(t_p3);
           }
           if (EXACT) {  // (unconditional: the previous step's slice is dead from here, the registers are free before)
 #pragma unroll
@@ -861,6 +868,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
             { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
             const bool live = has && sc[Y::sFLAG] == 0.0;
             if (live) {
+              CG_PIPE_WORK_BEGIN;
               stage_dhdu(blk, sc, sc + Y::sXH, n);
               double w[Q], f1[Q], fx[Q];
               vec_load(0, g, f1);
@@ -906,8 +914,9 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
 #pragma unroll
                 for (int q = 0; q < Q; q++) part += w[q] * w[q];
                 const double hn = sqrt(fast::warp_sum(part));  // gmres.hpp:59-60
-                finish_iter(kc, blk, g, n, hn, w, hc);
+                { CG_PIPE_WORK_BEGIN; finish_iter(kc, blk, g, n, hn, w, hc); CG_PIPE_WORK_END(t_fi); }
               }
+              CG_PIPE_WORK_END(t_it);
             }
             if (!EXACT) {
               if (k + 1 < km)
@@ -998,10 +1007,15 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
       a.dbg[48] = t_sw;
       a.dbg[49] = t_sum;
     }
-    if (wid == 1) {
+    if (wid == NG) {  // the first vector warp
       a.dbg[51] = t_dh;
       a.dbg[52] = t_fin;
       a.dbg[53] = t_si;
+      a.dbg[54] = t_p1;
+      a.dbg[55] = t_p2;
+      a.dbg[56] = t_p3;
+      a.dbg[57] = t_it;
+      a.dbg[58] = t_fi;
     }
   }
 #endif

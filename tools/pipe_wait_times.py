@@ -31,7 +31,9 @@ for w in range(24):
         print(f"warp {w:2d} ({role}): total {t[2*w+1]:8d} cycles, blocked at barriers {t[2*w]:8d} = {100.0*t[2*w]/t[2*w+1]:.1f} %")
 if os.environ.get("CGMRES_B200_PIPE_GEN") != "2":
     print(f"serial warp 0: inside sweeps {t[48]} cycles, inside sequential sums {t[49]} (sum over its rounds)")
-    print(f"vector warp 0 (warp 1): stage-parallel dHdu {t[51]}, final updates {t[52]}, state in {t[53]}")
+    print(f"first vector warp: stage-parallel dHdu {t[51]}, final updates {t[52]}, state in {t[53]}")
+    print(f"first vector warp, phases incl. their dHdu: after sweep 1 {t[54]}, after sweep 2 {t[55]}, after sweep 3 {t[56]}, "
+          f"Arnoldi phases {t[57]} (of which reflectors / v store / next input {t[58]})")
     sys.exit(0)
 if t[48]:
     print(f"serial warp 0: first pass {t[48]} cycles, second pass {t[49]}, Arnoldi sweeps {t[50]} (sum over its rounds)")
