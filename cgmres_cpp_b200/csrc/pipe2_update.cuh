@@ -942,6 +942,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
                 { CG_PIPE_WAIT_BEGIN; bar_sync(BL(g), T); CG_PIPE_WAIT_END(t_wait); }
                 const bool live = has && sc[Y::sFLAG] == 0.0;
                 if (live) {
+                  CG_PIPE_WORK_BEGIN;
                   const double hik = sc[Y::sRED];
                   double* w = W[EXACT ? g : 0];
                   __syncwarp();
@@ -961,6 +962,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
                     }
                   }
                   __syncwarp();
+                  CG_PIPE_WORK_END(t_mg);
                 }
                 bar_arrive(BX(g), T);
               }
@@ -980,7 +982,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
                 for (int i = 0; i < km + 2; i++) hc[i] = (i <= k) ? sc[Y::sHC + i] : 0.0;
                 const double hn = sqrt(sc[Y::sRED]);  // gmres.hpp:59-60
                 __syncwarp();
-                finish_iter(kc, blk, g, n, hn, W[EXACT ? g : 0], hc);
+                { CG_PIPE_WORK_BEGIN; finish_iter(kc, blk, g, n, hn, W[EXACT ? g : 0], hc); CG_PIPE_WORK_END(t_fi); }
               }
               if (k + 1 < km)
                 bar_arrive(BX(g), T);
@@ -1016,6 +1018,7 @@ __global__ void __launch_bounds__(Lay<M, EXACT>::threads, 1) control_kernel(cons
       a.dbg[56] = t_p3;
       a.dbg[57] = t_it;
       a.dbg[58] = t_fi;
+      a.dbg[59] = t_mg;
     }
   }
 #endif

@@ -33,7 +33,8 @@ if os.environ.get("CGMRES_B200_PIPE_GEN") != "2":
     print(f"serial warp 0: inside sweeps {t[48]} cycles, inside sequential sums {t[49]} (sum over its rounds)")
     print(f"first vector warp: stage-parallel dHdu {t[51]}, final updates {t[52]}, state in {t[53]}")
     print(f"first vector warp, phases incl. their dHdu: after sweep 1 {t[54]}, after sweep 2 {t[55]}, after sweep 3 {t[56]}, "
-          f"Arnoldi phases {t[57]} (of which reflectors / v store / next input {t[58]})")
+          f"Arnoldi phases {t[57]} (reflectors / v store / next input {t[58]}; bit-exact build: the phases between "
+          f"the sequential sums {t[59]})")
     sys.exit(0)
 if t[48]:
     print(f"serial warp 0: first pass {t[48]} cycles, second pass {t[49]}, Arnoldi sweeps {t[50]} (sum over its rounds)")
