@@ -67,10 +67,12 @@ struct Lay {
   static constexpr int XT = compact ? (dv + 1) * nx : F::XT;
   static constexpr int LTN = compact ? 0 : F::LTN;
   static_assert(F::SU == nu, "unpadded dim_u rows");
+  // instances per group = vector warps per CTA: 16 (18 warps, 96 registers), but 12 for a model whose sweep stage is
+  // register-hungry (the arm model's sin/cos): 14 warps = at most 4 per scheduler = 128 registers, no spills
 #ifndef CG_PIPE2_GI
-#define CG_PIPE2_GI 16
+#define CG_PIPE2_GI(NX, NU) (((NX) > 2 && (NU) < 4) ? 12 : 16)
 #endif
-  static constexpr int GI = CG_PIPE2_GI;  // instances per group = vector warps per CTA
+  static constexpr int GI = CG_PIPE2_GI(nx, nu);
   // per-instance shared-memory block (doubles)
   static constexpr int oX = 0;          // sweep input U (+ h*v) -> F in place; EXACT: element products of a sum
   static constexpr int oXT = oX + L;    // rollout states xtau[1..dv-1] (padded rows)

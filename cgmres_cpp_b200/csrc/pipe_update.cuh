@@ -43,7 +43,9 @@ namespace pipe {
 #define CG_PIPE_NGMAX 2
 #endif
 #ifndef CG_PIPE_GI
-#define CG_PIPE_GI 16  // instances per group = vector warps per CTA
+// instances per group = vector warps per CTA: 16, but 12 for a model whose sweep stage is register-hungry (the arm
+// model's sin/cos): 16 instead of 20 warps = 128 instead of 96 registers per thread, no spills
+#define CG_PIPE_GI(NX, NU) (((NX) > 2 && (NU) < 4) ? 12 : 16)
 #endif
 
 template <class M>
@@ -52,7 +54,7 @@ struct Lay {
   static constexpr int nx = F::nx, nu = F::nu, np = F::np, dv = F::dv, km = F::km, L = F::L, np1 = F::np1;
   static constexpr int SXT = F::SXT, XT = F::XT, LTN = F::LTN, Q = F::Q;
   static_assert(F::SU == nu, "pipelined kernel assumes unpadded dim_u rows");
-  static constexpr int GI = CG_PIPE_GI;
+  static constexpr int GI = CG_PIPE_GI(nx, nu);
   // groups in flight per SM: as many as fit in shared memory (each brings its own serial warp), at most CG_PIPE_NGMAX
   static constexpr int raw_ = L + XT + LTN + (km * (km + 1) / 2 + 3 * km + 3 * nx + np1 + 2 + km + 1 + 2);
   static constexpr int stride_ = (raw_ % 2 == 0) ? raw_ + 1 : raw_;
