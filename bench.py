@@ -357,16 +357,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         runs[m]["total_ms_max"] = v
     # ---- parity pass: every candidate against the bit-exact anchor at EVERY step of the same closed loop ---------------
     drift = {}
+    # the north star's closed-loop bar is "over 1000 steps": a shorter timed window does not shorten the parity horizon
+    parity_steps = args.parity_steps or max(warmup + steps, 1000)
     if anchor is not None and not args.no_parity:
-        drift, ends = trajectory_drift(lambda m: B.controller(model, n, m, batch), cand, anchor, warmup + steps, n,
+        drift, ends = trajectory_drift(lambda m: B.controller(model, n, m, batch), cand, anchor, parity_steps, n,
                                        MODEL_ROW_DOUBLES[model])
-        for m in cand:  # the logged run and the timed run are the same closed loop: same end state, bit for bit
-            if not np.array_equal(ends[m], runs[m]["x_end"]):
-                raise SystemExit(f"bench.py: mode {m}: the logged closed loop ended elsewhere than the timed one")
+        if parity_steps == warmup + steps:
+            for m in cand:  # the logged run and the timed run are the same closed loop: same end state, bit for bit
+                if not np.array_equal(ends[m], runs[m]["x_end"]):
+                    raise SystemExit(f"bench.py: mode {m}: the logged closed loop ended elsewhere than the timed one")
     for m in cand:
         if anchor is not None and m in drift:
             ps = drift_stats(drift[m])
-            ps["what"] = f"max over every step t <= {warmup + steps} and every state component of |x - x_anchor|"
+            ps["what"] = f"max over every step t <= {parity_steps} and every state component of |x - x_anchor|"
         elif anchor is not None:
             ps = parity_stats(runs[m]["x_end"], runs[anchor]["x_end"])
             ps["what"] = "end states only (--no-parity)"
@@ -553,7 +556,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                       "step); no flush needed",
                 "inputs": "seeded synthetic x0/p of SURVEY 8(d), u0 shipped + init_u0_newton(10)",
                 "mode_selection": "fastest candidate mode with zero instances above the 1e-6 closed-loop bar at any of "
-                                  "the warmup+steps steps, on the full batch, measured in this run (see `modes`)",
+                                  "the max(warmup+steps, 1000) steps of the parity pass, on the full batch, measured in "
+                                  "this run (see `modes`)",
             },
             "p50_launch_latency_ms": p50_ms,
             "p50_launch_latency_note": "median device time of ONE single-step launch of the whole batch (100 launches "
@@ -626,6 +630,8 @@ def main():
     ap.add_argument("--cpu-instances-per-core", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-modes", action="store_true", help="time only one bit-exact mode (+ fast)")
+    ap.add_argument("--parity-steps", type=int, default=0,
+                    help="closed-loop steps of the every-step parity pass (default: max(warmup + steps, 1000))")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the every-step parity pass (end states only; with an explicit non-exact --mode: no anchor run)")
     ap.add_argument("--no-configs", action="store_true", help="skip the arm / semiactive / mixed config runs")
